@@ -1,0 +1,385 @@
+"""Generate the golden fixtures of tests/golden/ by EXECUTING THE REFERENCE.
+
+Run in the build container only (needs /root/reference, read-only):
+    python tests/golden/make_golden.py
+Nothing here is imported by the product or by the GPU-box tests; the fixtures it writes
+are small torch.save files of plain tensors / lists / dicts (weights_only-loadable).
+
+What is executed from the reference, unmodified:
+  * Classification/unlearn/sfron.py  SFRon.prepare_unlearn + get_unlearned_model  (whole method)
+  * Classification/unlearn/salun.py  SalUn.get_gradient_ratio                     (global top-k)
+  * DDPM/generate_fisher_mask.py, SD/train-scripts/generate_fisher_mask.py        (as subprocesses)
+  * DiT/generate_mask.py main()
+  * DDPM/models/ema.py EMAHelper, DDPM/functions/__init__.py get_optimizer
+  * DiT/forget.py update_ema / cosine_lr_scheduler (function bodies extracted with `ast`,
+    because the module imports diffusers at top level, absent here)
+The forget-loop bodies of DDPM/runners/diffusion.py:1122-1180 and DiT/forget.py:285-322 are
+inline in 1000-line methods that need datasets and full-size models; for those the script
+drives the reference's OWN optimizer / EMA objects with synthetic gradients in the order of
+the cited lines.
+"""
+from __future__ import annotations
+
+import argparse
+import ast
+import importlib
+import os
+import subprocess
+import sys
+import tempfile
+import types
+
+import torch
+import torch.nn as nn
+import yaml
+
+REF = os.environ.get("SFR_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def flat(tensors):
+    return torch.cat([t.detach().reshape(-1).float() for t in tensors])
+
+
+class TinyNet(nn.Module):
+    """554 parameters: conv 3->8 (216+8) and fc 32->10 (320+10)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv = nn.Conv2d(3, 8, 3, padding=1)
+        self.fc = nn.Linear(32, 10)
+
+    def forward(self, x):
+        x = torch.relu(self.conv(x))
+        x = torch.nn.functional.adaptive_avg_pool2d(x, 2).flatten(1)
+        return self.fc(x)
+
+
+def loaders(seed):
+    g = torch.Generator().manual_seed(seed)
+    fx, fy = torch.randn(12, 3, 8, 8, generator=g), torch.randint(0, 10, (12,), generator=g)
+    rx, ry = torch.randn(16, 3, 8, 8, generator=g), torch.randint(0, 10, (16,), generator=g)
+    from torch.utils.data import DataLoader, TensorDataset
+    mk = lambda x, y: DataLoader(TensorDataset(x, y), batch_size=4, shuffle=False)
+    return dict(forget_train=mk(fx, fy), retain_train=mk(rx, ry), forget_valid=None, retain_valid=None)
+
+
+class GradRecorder:
+    """Records the raw gradient of every backward pass through tensor hooks."""
+
+    def __init__(self, model):
+        self.names = [n for n, _ in model.named_parameters()]
+        self.records = []
+        self._cur = {}
+        for n, p in model.named_parameters():
+            p.register_hook(self._hook(n))
+
+    def _hook(self, name):
+        def fn(grad):
+            self._cur[name] = grad.detach().clone()
+            if len(self._cur) == len(self.names):
+                self.records.append(flat([self._cur[n] for n in self.names]))
+                self._cur = {}
+        return fn
+
+
+# ------------------------------------------------------------------------------- Classification
+def import_classification():
+    sys.path.insert(0, os.path.join(REF, "Classification"))
+    torch.Tensor.cuda = lambda self, *a, **k: self          # the reference hard-codes .cuda()
+    nn.Module.cuda = lambda self, *a, **k: self
+    import unlearn  # the reference package
+    return unlearn
+
+
+def classification(tag, ema_beta, n_iters=10, forget_freq=3):
+    unlearn = import_classification()
+
+    torch.manual_seed(0)
+    model = TinyNet()
+    names = [n for n, _ in model.named_parameters()]
+    shapes = {n: list(p.shape) for n, p in model.named_parameters()}
+    theta0 = flat(model.parameters())
+    rec = GradRecorder(model)
+
+    lrs = []
+    orig_step = torch.optim.SGD.step
+
+    def logging_step(self, *a, **k):
+        lrs.append(self.param_groups[0]["lr"])
+        return orig_step(self, *a, **k)
+
+    with tempfile.TemporaryDirectory() as tmp:
+        args = argparse.Namespace(num_classes=10, seed=0)
+        method = unlearn.create_unlearn_method("SFRon")(model, nn.CrossEntropyLoss(), tmp, args)
+        method.n_iters, method.forget_freq, method.log_freq = n_iters, forget_freq, 10 ** 9
+        method.ema_beta = ema_beta
+        dls = loaders(1)
+        method.prepare_unlearn(dls)
+        n_fisher = len(rec.records)
+        ff = torch.load(os.path.join(tmp, "forget_fisher.pt"))
+        rf = torch.load(os.path.join(tmp, "remain_fisher.pt"))
+        mask = method.weight_saliency_mask
+        torch.optim.SGD.step = logging_step
+        try:
+            method.get_unlearned_model()
+        finally:
+            torch.optim.SGD.step = orig_step
+    nf, nr = len(dls["forget_train"]), len(dls["retain_train"])
+    assert n_fisher == nf + nr
+    loop = rec.records[n_fisher:]
+    kinds = []
+    for step in range(n_iters):
+        if step % forget_freq == 0:
+            kinds.append("forget")
+        kinds.append("remain")
+    assert len(kinds) == len(loop) == len(lrs)
+    fixture = dict(
+        names=names, shapes=shapes, theta0=theta0,
+        fisher_forget_grads=torch.stack(rec.records[:nf]), fisher_remain_grads=torch.stack(rec.records[nf:n_fisher]),
+        forget_fisher=flat([ff[n] for n in names]), remain_fisher=flat([rf[n] for n in names]),
+        mask=torch.cat([mask[n].reshape(-1) for n in names]).to(torch.uint8), threshold=float(method.th),
+        loop_kinds=kinds, loop_lrs=[float(x) for x in lrs], loop_grads=torch.stack(loop),
+        theta_final=flat(model.parameters()),
+        hyper=dict(momentum=method.momentum, weight_decay=method.weight_decay, max_norm=method.max_norm,
+                   ema_beta=float(ema_beta), n_iters=n_iters, forget_freq=forget_freq,
+                   retain_lr=method.retain_lr, forget_alpha=float(method.forget_alpha)),
+    )
+    torch.save(fixture, os.path.join(OUT, f"cls_sfron_{tag}.pt"))
+    print("wrote", tag, "N =", theta0.numel(), "loop records", len(loop))
+
+
+def salun_topk():
+    unlearn = import_classification()
+    out = {}
+    for th in (0.2, 0.5):
+        torch.manual_seed(3)
+        model = TinyNet()
+        names = [n for n, _ in model.named_parameters()]
+        rec = GradRecorder(model)
+        args = argparse.Namespace(num_classes=10, seed=0, batch_size=4)
+        with tempfile.TemporaryDirectory() as tmp:
+            method = unlearn.create_unlearn_method("SalUn")(model, nn.CrossEntropyLoss(), tmp, args)
+            method.th = th
+            hard = method.get_gradient_ratio(loaders(2)["forget_train"])
+        out[str(th)] = dict(grads=torch.stack(rec.records),
+                            mask=torch.cat([hard[n].reshape(-1) for n in names]),
+                            mask_dtype=str(hard[names[0]].dtype))
+    out["names"] = names
+    out["shapes"] = {n: list(p.shape) for n, p in model.named_parameters()}
+    torch.save(out, os.path.join(OUT, "salun_topk.pt"))
+    print("wrote salun_topk")
+
+
+# --------------------------------------------------------------------------- ratio-mask scripts
+def synthetic_fishers(seed, names_shapes, placeholder=None):
+    g = torch.Generator().manual_seed(seed)
+    ff, rf = {}, {}
+    for name, shape in names_shapes:
+        if name == placeholder:
+            ff[name], rf[name] = 0, 0           # never received a gradient (DiT pos_embed)
+            continue
+        a = (torch.randn(8, *shape, generator=g) * 1e-3).pow(2).mean(0)
+        b = (torch.randn(8, *shape, generator=g) * 1e-3).pow(2).mean(0)
+        fa, fb = a.reshape(-1), b.reshape(-1)
+        k = max(1, fa.numel() // 7)
+        fa[:k] = 0.0                              # exact zeros on one side
+        fb[k:2 * k] = 0.0
+        fa[2 * k:3 * k] = 0.0
+        fb[2 * k:3 * k] = 0.0                     # 0/0 -> eps/eps == 1.0 : hits `>= 1.0` exactly
+        fb[3 * k:4 * k] = fa[3 * k:4 * k]          # ratio exactly 1
+        ff[name], rf[name] = a, b
+    return ff, rf
+
+
+SHAPES = [("module.pos_embed", (1, 6, 8)), ("module.conv.weight", (8, 3, 3, 3)), ("module.conv.bias", (8,)),
+          ("module.fc.weight", (10, 33)), ("module.fc.bias", (3,)), ("module.scale", ())]
+
+
+def ratio_script(script, ff_name, rf_name, out_fmt, tag, thresholds):
+    ff, rf = synthetic_fishers(11, SHAPES[1:])
+    res = {"forget": ff, "remain": rf, "masks": {}}
+    with tempfile.TemporaryDirectory() as tmp:
+        torch.save(ff, os.path.join(tmp, ff_name))
+        torch.save(rf, os.path.join(tmp, rf_name))
+        for th in thresholds:
+            subprocess.run([sys.executable, os.path.join(REF, script), "--ckpt_folder", tmp,
+                            "--threshold", str(th)], check=True, stdout=subprocess.DEVNULL)
+            res["masks"][str(float(th))] = torch.load(os.path.join(tmp, out_fmt.format(th=float(th))))
+    torch.save(res, os.path.join(OUT, f"{tag}_ratio_mask.pt"))
+    print("wrote", tag, "ratio masks")
+
+
+def dit_masks():
+    sys.path.insert(0, os.path.join(REF, "DiT"))
+    gm = importlib.import_module("generate_mask")
+    ff, rf = synthetic_fishers(12, SHAPES, placeholder="module.pos_embed")
+    ths = [0.5, 1, 3, 5, 10]
+    res = {"forget": ff, "remain": rf, "masks": {}}
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "7"))
+        torch.save(ff, os.path.join(tmp, "7", "forget_fisher.pt"))
+        torch.save(rf, os.path.join(tmp, "7", "remain_fisher.pt"))
+        gm.main(argparse.Namespace(mask_path=tmp, forget_class=[7], thresholds=ths))
+        for th in ths:
+            res["masks"][str(th)] = torch.load(os.path.join(tmp, "7", f"fisher_{th}.pt"))
+    torch.save(res, os.path.join(OUT, "dit_ratio_mask.pt"))
+    print("wrote dit ratio masks")
+
+
+# ------------------------------------------------------------------------------- forget loops
+def extract_functions(path, wanted):
+    """Compile selected top-level function definitions of a reference file without importing it."""
+    tree = ast.parse(open(path).read())
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    mod = types.ModuleType("extracted")
+    import math
+    from collections import OrderedDict
+    mod.__dict__.update(torch=torch, math=math, OrderedDict=OrderedDict)
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), mod.__dict__)
+    return mod
+
+
+def synthetic_grads(gen, n, steps, scales):
+    return torch.stack([torch.randn(n, generator=gen) * scales[i % len(scales)] for i in range(steps)])
+
+
+def unflat_into_grads(model, vec):
+    off = 0
+    for p in model.parameters():
+        if p.requires_grad:
+            p.grad = vec[off:off + p.numel()].reshape(p.shape).clone()
+            off += p.numel()
+
+
+def ddpm_loop():
+    sys.path.insert(0, os.path.join(REF, "DDPM"))
+    from models.ema import EMAHelper            # reference class
+    from functions import get_optimizer         # reference helper
+
+    def d2n(d):
+        ns = argparse.Namespace()
+        for k, v in d.items():
+            setattr(ns, k, d2n(v) if isinstance(v, dict) else v)
+        return ns
+
+    config = d2n(yaml.safe_load(open(os.path.join(REF, "DDPM/configs/cifar10_sfron.yml"))))
+    torch.manual_seed(5)
+    model = nn.DataParallel(TinyNet())
+    names = [n for n, _ in model.named_parameters()]
+    n = sum(p.numel() for p in model.parameters())
+    theta0 = flat(model.parameters())
+    gen = torch.Generator().manual_seed(6)
+    mask = {nm: (torch.rand(p.shape, generator=gen) < 0.4) for nm, p in model.named_parameters()}
+    steps = 6
+    gf = synthetic_grads(gen, n, steps, [3.0, 0.01, 0.2])   # norm >1 and <1: both clip branches
+    gr = synthetic_grads(gen, n, steps, [0.02, 5.0])
+    optimizer = get_optimizer(config, model.parameters())
+    ema_helper = EMAHelper(mu=config.model.ema_rate)
+    ema_helper.register(model)
+    for step in range(steps):
+        # forget stage, runners/diffusion.py:1122-1138 (method "ron")
+        optimizer.zero_grad()
+        unflat_into_grads(model, gf[step])
+        for name, param in model.named_parameters():
+            if param.grad is not None:
+                param.grad *= mask[name].to(param.grad.device)
+        torch.nn.utils.clip_grad_norm_(model.parameters(), config.optim.grad_clip)
+        optimizer.step()
+        # remain stage, :1156-1176
+        optimizer.zero_grad()
+        unflat_into_grads(model, gr[step])
+        torch.nn.utils.clip_grad_norm_(model.parameters(), config.optim.grad_clip)
+        optimizer.step()
+        # :1179-1180
+        ema_helper.update(model)
+    st = optimizer.state
+    fixture = dict(names=names, shapes={nm: list(p.shape) for nm, p in model.named_parameters()},
+                   theta0=theta0, mask=torch.cat([mask[nm].reshape(-1) for nm in names]).to(torch.uint8),
+                   forget_grads=gf, remain_grads=gr, theta_final=flat(model.parameters()),
+                   exp_avg=flat([st[p]["exp_avg"] for p in model.parameters()]),
+                   exp_avg_sq=flat([st[p]["exp_avg_sq"] for p in model.parameters()]),
+                   ema_final=flat([ema_helper.shadow[nm] for nm, _ in model.module.named_parameters()]),
+                   hyper=dict(lr=config.optim.lr, beta1=config.optim.beta1, beta2=0.999, eps=config.optim.eps,
+                              weight_decay=config.optim.weight_decay, grad_clip=config.optim.grad_clip,
+                              ema_rate=config.model.ema_rate))
+    torch.save(fixture, os.path.join(OUT, "ddpm_adam_ema_loop.pt"))
+    print("wrote ddpm loop")
+
+
+class TinyDiT(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.pos_embed = nn.Parameter(torch.randn(1, 6, 8), requires_grad=False)   # DiT/models.py:176
+        self.fc = nn.Linear(33, 10)
+        self.out = nn.Linear(10, 4)
+
+
+def dit_loop():
+    ex = extract_functions(os.path.join(REF, "DiT/forget.py"), {"update_ema", "cosine_lr_scheduler"})
+    torch.manual_seed(7)
+    from copy import deepcopy
+    model = TinyDiT()
+    ema = deepcopy(model)
+    for p in ema.parameters():
+        p.requires_grad = False
+    model = nn.DataParallel(model)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0)     # DiT/forget.py:199
+    ex.update_ema(ema, model.module, decay=0)                                  # :230
+    names = [n for n, _ in model.named_parameters()]
+    train_names = [n for n, p in model.named_parameters() if p.requires_grad]
+    n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    theta0 = flat(model.parameters())
+    gen = torch.Generator().manual_seed(8)
+    mask = {nm: ((torch.rand(p.shape, generator=gen) < 0.5) if p.requires_grad else 0)
+            for nm, p in model.named_parameters()}
+    steps = 5
+    gf = synthetic_grads(gen, n_train, steps, [2.0, 0.05])
+    gr = synthetic_grads(gen, n_train, steps, [0.3])
+    for step in range(steps):
+        # DiT/forget.py:285-299
+        opt.zero_grad()
+        unflat_into_grads(model, gf[step])
+        for name, param in model.named_parameters():
+            if param.grad is not None:
+                param.grad *= mask[name].to(param.grad.device)
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        # :310-320 (no clip on the remain step)
+        opt.zero_grad()
+        unflat_into_grads(model, gr[step])
+        opt.step()
+        ex.update_ema(ema, model.module)                                       # :322
+    fixture = dict(names=names, train_names=train_names,
+                   shapes={nm: list(p.shape) for nm, p in model.named_parameters()},
+                   theta0=theta0, forget_grads=gf, remain_grads=gr,
+                   mask=torch.cat([mask[nm].reshape(-1) for nm in train_names]).to(torch.uint8),
+                   theta_final=flat(model.parameters()), ema_final=flat(ema.parameters()),
+                   cosine=[ex.cosine_lr_scheduler(25.0, t, 10) for t in range(10)],
+                   hyper=dict(lr=1e-4, weight_decay=0.0, grad_clip=1.0, decay=0.9999))
+    torch.save(fixture, os.path.join(OUT, "dit_adamw_ema_loop.pt"))
+    print("wrote dit loop")
+
+
+PARTS = {
+    "cls_default": lambda: classification("default", ema_beta=1.0),
+    "cls_beta09": lambda: classification("beta09", ema_beta=0.9),
+    "salun": salun_topk,
+    "ddpm_mask": lambda: ratio_script("DDPM/generate_fisher_mask.py", "forget_fisher.pt", "remain_fisher.pt",
+                                      "fisher_{th}.pt", "ddpm", [1.0, 0.5, 3.0]),
+    "sd_mask": lambda: ratio_script("SD/train-scripts/generate_fisher_mask.py", "nude_forget.pt",
+                                    "nude_remain.pt", "nude_mask_{th}.pt", "sd", [1.0]),
+    "dit_mask": dit_masks,
+    "ddpm_loop": ddpm_loop,
+    "dit_loop": dit_loop,
+}
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)
+    if len(sys.argv) > 1:
+        PARTS[sys.argv[1]]()
+    else:
+        # one interpreter per part: the reference's sub-projects reuse top-level module names
+        # (`models`, `utils`, `functions`) and cannot share a sys.modules
+        for part in PARTS:
+            subprocess.run([sys.executable, os.path.abspath(__file__), part], check=True)

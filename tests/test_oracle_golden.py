@@ -1,0 +1,119 @@
+"""Pins the CPU oracle against outputs of the REFERENCE ITSELF (tests/golden/*.pt, produced by
+tests/golden/make_golden.py from /root/reference).  CPU only."""
+import pytest
+import torch
+
+from conftest import bits_equal, load_golden, max_rel_err, unflat
+from oracle import sfron_oracle as O
+
+RTOL = 1e-6  # north-star tolerance for fp32 values; masks must be bit-exact
+
+
+def _close(a, b):
+    return max_rel_err(a, b, floor=1e-12) <= RTOL
+
+
+@pytest.mark.parametrize("tag", ["default", "beta09"])
+def test_classification_sfron_replay(tag):
+    fx = load_golden(f"cls_sfron_{tag}.pt")
+    names, shapes, hp = fx["names"], fx["shapes"], fx["hyper"]
+    # Fisher: F += grad**2 / len(loader)  (sfron.py:288-291,315-318)
+    for which in ("forget", "remain"):
+        grads = fx[f"fisher_{which}_grads"]
+        acc = O.fisher_init(names)
+        for g in grads:
+            O.fisher_accumulate(acc, unflat(g, names, shapes), len(grads))
+        got = torch.cat([acc[n].reshape(-1) for n in names])
+        assert bits_equal(got, fx[f"{which}_fisher"]), f"{which} Fisher differs from the reference run"
+    # ratio mask (sfron.py:322-336)
+    ff, rf = unflat(fx["forget_fisher"], names, shapes), unflat(fx["remain_fisher"], names, shapes)
+    masks, zeros, total = O.ratio_mask(ff, rf, fx["threshold"])
+    got = torch.cat([masks[n].reshape(-1) for n in names]).to(torch.uint8)
+    assert torch.equal(got, fx["mask"])
+    assert total == got.numel() and zeros == int((got == 0).sum())
+    # forget / remain loop with slow-fast interpolation (sfron.py:189-259)
+    loop = O.FlatReferenceLoop(shapes, unflat(fx["theta0"], names, shapes), "sgd",
+                               dict(lr=hp["retain_lr"], momentum=hp["momentum"], weight_decay=hp["weight_decay"]),
+                               ema_mode="slowfast", ema_a=hp["ema_beta"])
+    for kind, lr, g in zip(fx["loop_kinds"], fx["loop_lrs"], fx["loop_grads"]):
+        loop.set_lr(lr)
+        gd = unflat(g, names, shapes)
+        if kind == "forget":
+            loop.forget_step(gd, mask=masks, max_norm=hp["max_norm"])
+        else:
+            loop.remain_step(gd, ema=True)
+    assert _close(loop.flat("p"), fx["theta_final"]), max_rel_err(loop.flat("p"), fx["theta_final"])
+
+
+def test_salun_topk_mask():
+    fx = load_golden("salun_topk.pt")
+    names, shapes = fx["names"], fx["shapes"]
+    for th in ("0.2", "0.5"):
+        rec = fx[th]
+        acc = rec["grads"].sum(0) if rec["grads"].shape[0] == 1 else None
+        # `gradients[name] += param.grad.data` per batch, then abs_ (salun.py:158-165)
+        tot = torch.zeros_like(rec["grads"][0])
+        for g in rec["grads"]:
+            tot += g
+        grads = unflat(tot.abs(), names, shapes)
+        assert rec["mask_dtype"] == "torch.int64"
+        for stable in (True, False):
+            hard = O.topk_mask(grads, float(th), stable=stable)
+            got = torch.cat([hard[n].reshape(-1) for n in names])
+            assert got.dtype == torch.int64
+            assert torch.equal(got, rec["mask"]), f"th={th} stable={stable}"
+        flat = O.topk_mask_flat(tot, int(tot.numel() * float(th)))
+        assert torch.equal(flat.to(torch.int64), rec["mask"])
+
+
+@pytest.mark.parametrize("fixture", ["ddpm_ratio_mask.pt", "sd_ratio_mask.pt", "dit_ratio_mask.pt"])
+def test_ratio_mask_scripts(fixture):
+    fx = load_golden(fixture)
+    for th_s, ref_masks in fx["masks"].items():
+        th = float(th_s)
+        masks, zeros, total = O.ratio_mask(fx["forget"], fx["remain"], th)
+        assert list(masks.keys()) == list(ref_masks.keys())
+        for name, ref in ref_masks.items():
+            if torch.is_tensor(ref):
+                assert masks[name].dtype == torch.bool and torch.equal(masks[name], ref), (th, name)
+            else:
+                assert masks[name] == 0 and ref == 0      # int placeholder for grad-less params
+        assert total == sum(m.numel() for m in ref_masks.values() if torch.is_tensor(m))
+
+
+def test_ddpm_adam_ema_loop():
+    fx = load_golden("ddpm_adam_ema_loop.pt")
+    names, shapes, hp = fx["names"], fx["shapes"], fx["hyper"]
+    loop = O.FlatReferenceLoop(shapes, unflat(fx["theta0"], names, shapes), "adam",
+                               dict(lr=hp["lr"], beta1=hp["beta1"], beta2=hp["beta2"], eps=hp["eps"],
+                                    weight_decay=hp["weight_decay"]), ema_mode="ddpm", ema_a=hp["ema_rate"])
+    mask = {n: m.bool() for n, m in unflat(fx["mask"], names, shapes).items()}
+    for gf, gr in zip(fx["forget_grads"], fx["remain_grads"]):
+        loop.forget_step(unflat(gf, names, shapes), mask=mask, max_norm=hp["grad_clip"])
+        loop.remain_step(unflat(gr, names, shapes), max_norm=hp["grad_clip"], ema=True)
+    assert _close(loop.flat("p"), fx["theta_final"])
+    assert _close(loop.flat("m"), fx["exp_avg"])
+    assert _close(loop.flat("v"), fx["exp_avg_sq"])
+    assert _close(loop.flat("slow"), fx["ema_final"])
+
+
+def test_dit_adamw_ema_loop():
+    fx = load_golden("dit_adamw_ema_loop.pt")
+    names, tnames, shapes, hp = fx["names"], fx["train_names"], fx["shapes"], fx["hyper"]
+    theta0 = unflat(fx["theta0"], names, shapes)
+    loop = O.FlatReferenceLoop({n: shapes[n] for n in tnames}, theta0, "adamw",
+                               dict(lr=hp["lr"], weight_decay=hp["weight_decay"]), ema_mode="dit", ema_a=hp["decay"])
+    tshapes = {n: shapes[n] for n in tnames}
+    mask = {n: m.bool() for n, m in unflat(fx["mask"], tnames, tshapes).items()}
+    frozen = {n: theta0[n] for n in names if n not in tnames}
+    frozen_ema = {n: t.clone() for n, t in frozen.items()}
+    for gf, gr in zip(fx["forget_grads"], fx["remain_grads"]):
+        loop.forget_step(unflat(gf, tnames, tshapes), mask=mask, max_norm=hp["grad_clip"])
+        loop.remain_step(unflat(gr, tnames, tshapes), max_norm=None, ema=True)
+        O.ema_dit_(frozen_ema, frozen, hp["decay"])      # update_ema walks ALL parameters
+    got_p = torch.cat([(loop.params[n].detach() if n in tnames else frozen[n]).reshape(-1) for n in names])
+    got_e = torch.cat([(loop.slow[n] if n in tnames else frozen_ema[n]).reshape(-1) for n in names])
+    assert _close(got_p, fx["theta_final"])
+    assert _close(got_e, fx["ema_final"])
+    for t, ref in enumerate(fx["cosine"]):
+        assert O.cosine_lr_scheduler(25.0, t, 10) == ref

@@ -1,0 +1,160 @@
+// common.cuh — shared device helpers for the SFR-on hot-path kernels (sm_100a).
+//
+// Every kernel on this path is an HBM-bound stream over a flat parameter shard:
+//   * 128-bit coalesced accesses (one float4 per thread per access, a warp covers
+//     512 contiguous bytes), several independent accesses in flight per thread;
+//   * streaming cache hints (ld.global.cs / st.global.cs): every byte is touched once
+//     per launch, so nothing is worth keeping in L1 and L2 should evict it first;
+//   * persistent grid = SMs x resident CTAs, tiles handed out grid-stride;
+//   * reductions: warp shuffle -> shared memory -> ONE atomic per CTA.
+// No fast-math: the file is compiled with -fmad=false and uses explicit
+// __f*_rn / __fmaf_rn so the rounding sequence is exactly the one documented in
+// DESIGN.md ("Arithmetic contract").
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sfron_b200.h"
+
+namespace sfr {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// ---- launch geometry --------------------------------------------------------
+struct DeviceGeometry {
+  int sm_count = 0;
+  int cc_major = 0;
+  int cc_minor = 0;
+  bool ok = false;
+};
+
+// Cached per process (one GPU per process in this framework).
+const DeviceGeometry& device_geometry();
+
+// Persistent grid: enough CTAs to fill every SM `ctas_per_sm` times, but never more
+// than there are tiles.
+inline int persistent_grid(int64_t tiles, int ctas_per_sm) {
+  const DeviceGeometry& g = device_geometry();
+  int64_t cap = (int64_t)(g.sm_count > 0 ? g.sm_count : 148) * ctas_per_sm;
+  if (tiles < 1) tiles = 1;
+  return (int)(tiles < cap ? tiles : cap);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- streaming vector access ---------------------------------------------------
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+
+__device__ __forceinline__ float bf16_bits_to_f32(uint32_t b16) { return __uint_as_float(b16 << 16); }
+
+// Four consecutive gradients starting at element 4*vec, as fp32.
+template <int GT>
+__device__ __forceinline__ float4 load_g4(const void* g, int64_t vec) {
+  if constexpr (GT == SFR_F32) {
+    return __ldcs(reinterpret_cast<const float4*>(g) + vec);
+  } else {
+    uint2 raw = __ldcs(reinterpret_cast<const uint2*>(g) + vec);
+    float4 r;
+    r.x = bf16_bits_to_f32(raw.x & 0xffffu);
+    r.y = bf16_bits_to_f32(raw.x >> 16);
+    r.z = bf16_bits_to_f32(raw.y & 0xffffu);
+    r.w = bf16_bits_to_f32(raw.y >> 16);
+    return r;
+  }
+}
+template <int GT>
+__device__ __forceinline__ float load_g1(const void* g, int64_t i) {
+  if constexpr (GT == SFR_F32) {
+    return __ldcs(reinterpret_cast<const float*>(g) + i);
+  } else {
+    return bf16_bits_to_f32(__ldcs(reinterpret_cast<const unsigned short*>(g) + i));
+  }
+}
+template <int GT>
+__device__ __forceinline__ void zero_g4(void* g, int64_t vec) {
+  if constexpr (GT == SFR_F32) {
+    __stcs(reinterpret_cast<float4*>(g) + vec, make_float4(0.f, 0.f, 0.f, 0.f));
+  } else {
+    __stcs(reinterpret_cast<uint2*>(g) + vec, make_uint2(0u, 0u));
+  }
+}
+template <int GT>
+__device__ __forceinline__ void zero_g1(void* g, int64_t i) {
+  if constexpr (GT == SFR_F32) {
+    reinterpret_cast<float*>(g)[i] = 0.f;
+  } else {
+    reinterpret_cast<unsigned short*>(g)[i] = 0;
+  }
+}
+
+// Four mask bytes (0/1) for elements 4*vec .. 4*vec+3.
+__device__ __forceinline__ uint32_t load_mask4(const uint8_t* mask, int64_t vec) {
+  return __ldcs(reinterpret_cast<const unsigned int*>(mask) + vec);
+}
+__device__ __forceinline__ float mask_byte_to_f32(uint32_t packed, int lane) {
+  return (float)((packed >> (8 * lane)) & 0xffu);
+}
+
+// ---- clip coefficient ------------------------------------------------------------
+// torch.nn.utils.clip_grad_norm_:  coef = clamp(max_norm / (total_norm + 1e-6), max=1.0)
+// total_norm is formed from the double-precision sum of squares (at least as accurate
+// as torch's fp32 norm of per-tensor norms).
+__device__ __forceinline__ float clip_coef_from_sumsq(const double* sumsq, float max_norm) {
+  float total_norm = (float)sqrt(*sumsq);
+  float coef = __fdiv_rn(max_norm, __fadd_rn(total_norm, 1e-6f));
+  return coef > 1.0f ? 1.0f : coef;  // keeps NaN, like torch.clamp(max=1.0)
+}
+
+// ---- reductions -----------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+
+// Sum over the CTA; result valid in thread 0.  `scratch` holds >= 32 elements.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  T r = T(0);
+  if (warp == 0) {
+    const int nwarps = (blockDim.x + 31) >> 5;
+    r = lane < nwarps ? scratch[lane] : T(0);
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+// ---- order-preserving key of |x| (K2b) -----------------------------------------------
+// 0 for NaN (ranks last, never selected before any number), else bits(|x|) + 1.
+__device__ __forceinline__ uint32_t select_key(float x) {
+  uint32_t b = __float_as_uint(x) & 0x7fffffffu;
+  return b > 0x7f800000u ? 0u : b + 1u;
+}
+
+}  // namespace sfr
+
+// ---- host-side argument checks ---------------------------------------------------------
+#define SFR_REQUIRE_PTR(p) \
+  do {                     \
+    if ((p) == nullptr) return SFR_ERR_NULL; \
+  } while (0)
+#define SFR_REQUIRE_ALIGNED(p) \
+  do {                         \
+    if ((p) != nullptr && !sfr::aligned16(p)) return SFR_ERR_ALIGN; \
+  } while (0)
+#define SFR_LAUNCH_STATUS()                \
+  do {                                     \
+    cudaError_t e__ = cudaGetLastError();  \
+    return e__ == cudaSuccess ? SFR_OK : (int)e__; \
+  } while (0)

@@ -1,0 +1,514 @@
+// select.cu — K2b: exact global top-k saliency selection by a two-pass radix /
+// histogram select over order-preserving keys, plus the threshold apply.
+//
+// Reference (two full CPU argsorts of an N-element vector, 16 B/elem of index temporaries):
+//   all = -cat(|sum_batches g|); ranks = argsort(argsort(all)); mask = ranks < int(N*ratio)
+//     DDPM/runners/diffusion.py:1009-1034, Classification/unlearn/salun.py:170-193
+//   thr = -topk(-|theta - theta0|, k)[0][-1]      SD/train-scripts/proximal_gradient.py:161-165
+//
+// key(x) = 0 for NaN else bits(|x|)+1   (31 significant bits; monotone in |x|)
+//   pass 0: histogram of key[30:16] (32768 bins) in SHARED memory, one CTA per SM
+//   scan 0: largest bin B with  #(bin > B) < k  -> prefix, rank wanted inside B
+//   pass 1: histogram of key[15:0] for keys whose [30:16] == prefix (65536 global bins;
+//           only the few matching elements issue an atomic)
+//   scan 1: threshold key, #greater, #equal, tie budget
+//   apply : mask = key > thr  ||  (key == thr && index-ordered tie rank < budget)
+// Between hist and scan a multi-GPU caller all-reduces `bins` (<= 512 KB) over NCCL;
+// everything else is shard-local.  All steps are stream-ordered; the host never has to
+// read anything back.
+#include "common.cuh"
+
+namespace sfr {
+namespace {
+
+// ---- key source ------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ uint32_t key_from(float a, float b, float eps) {
+  if constexpr (MODE == SFR_KEY_ABS) {
+    return select_key(a);
+  } else {
+    return select_key(__fdiv_rn(__fadd_rn(a, eps), __fadd_rn(b, eps)));
+  }
+}
+
+// Per-thread run-length cache in front of an atomic histogram: consecutive items of one
+// thread that fall in the same bin cost one atomic.  Dead units give long runs of exact
+// zeros (a constructor-initialised DiT has 99.96 % zero gradients), which
+// would otherwise serialise on a single counter.
+template <typename Counter>
+struct RunCache {
+  uint32_t bin = 0xffffffffu;
+  uint32_t count = 0;
+  __device__ __forceinline__ void push(Counter* hist, uint32_t b) {
+    if (b == bin) {
+      ++count;
+    } else {
+      if (count) atomicAdd(hist + bin, (Counter)count);
+      bin = b;
+      count = 1;
+    }
+  }
+  __device__ __forceinline__ void flush(Counter* hist) {
+    if (count) atomicAdd(hist + bin, (Counter)count);
+    count = 0;
+    bin = 0xffffffffu;
+  }
+};
+
+// ---- pass 0: 15-bit shared-memory histogram ----------------------------------------------
+constexpr int kHistThreads = 1024;
+constexpr int kHistUnroll = 4;
+
+template <int MODE>
+__global__ void __launch_bounds__(kHistThreads, 1)
+select_hist0_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps, int64_t n,
+                    unsigned long long* __restrict__ bins) {
+  extern __shared__ unsigned int hist[];  // SFR_SELECT_BINS0 counters, 128 KB
+  for (int i = threadIdx.x; i < SFR_SELECT_BINS0; i += kHistThreads) hist[i] = 0;
+  __syncthreads();
+
+  const int64_t nvec = n >> 2;
+  const int64_t tile = (int64_t)kHistThreads * kHistUnroll;
+  const int64_t ntiles = (nvec + tile - 1) / tile;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  RunCache<unsigned int> rc;
+
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * tile + threadIdx.x;
+    float4 x[kHistUnroll], y[kHistUnroll];
+#pragma unroll
+    for (int u = 0; u < kHistUnroll; ++u) {
+      const int64_t v = base + (int64_t)u * kHistThreads;
+      const bool in = v < nvec;
+      x[u] = in ? ld_stream(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (MODE == SFR_KEY_RATIO)
+        y[u] = in ? ld_stream(b4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      else
+        y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kHistUnroll; ++u) {
+      const int64_t v = base + (int64_t)u * kHistThreads;
+      if (v >= nvec) continue;
+      rc.push(hist, key_from<MODE>(x[u].x, y[u].x, eps) >> 16);
+      rc.push(hist, key_from<MODE>(x[u].y, y[u].y, eps) >> 16);
+      rc.push(hist, key_from<MODE>(x[u].z, y[u].z, eps) >> 16);
+      rc.push(hist, key_from<MODE>(x[u].w, y[u].w, eps) >> 16);
+    }
+  }
+  const int64_t tail0 = nvec << 2;
+  if (blockIdx.x == 0 && threadIdx.x < (n - tail0)) {
+    const int64_t i = tail0 + threadIdx.x;
+    rc.push(hist, key_from<MODE>(a[i], MODE == SFR_KEY_RATIO ? b[i] : 0.f, eps) >> 16);
+  }
+  rc.flush(hist);
+  __syncthreads();
+  for (int i = threadIdx.x; i < SFR_SELECT_BINS0; i += kHistThreads) {
+    const unsigned int c = hist[i];
+    if (c) atomicAdd(bins + i, (unsigned long long)c);
+  }
+}
+
+// ---- pass 1: filtered 16-bit histogram straight into global bins -----------------------------
+constexpr int kFiltThreads = 256;
+constexpr int kFiltCtasPerSm = 4;
+constexpr int kFiltUnroll = 4;
+
+template <int MODE>
+__global__ void __launch_bounds__(kFiltThreads, kFiltCtasPerSm)
+select_hist1_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps, int64_t n,
+                    const sfr_select_state* __restrict__ state,
+                    unsigned long long* __restrict__ bins) {
+  if (state->select_none || state->select_all) return;
+  const uint32_t prefix = state->prefix;
+  const int64_t nvec = n >> 2;
+  const int64_t tile = (int64_t)kFiltThreads * kFiltUnroll;
+  const int64_t ntiles = (nvec + tile - 1) / tile;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  RunCache<unsigned long long> rc;
+
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * tile + threadIdx.x;
+    float4 x[kFiltUnroll], y[kFiltUnroll];
+#pragma unroll
+    for (int u = 0; u < kFiltUnroll; ++u) {
+      const int64_t v = base + (int64_t)u * kFiltThreads;
+      const bool in = v < nvec;
+      x[u] = in ? ld_stream(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (MODE == SFR_KEY_RATIO)
+        y[u] = in ? ld_stream(b4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      else
+        y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kFiltUnroll; ++u) {
+      const int64_t v = base + (int64_t)u * kFiltThreads;
+      if (v >= nvec) continue;
+      const uint32_t k0 = key_from<MODE>(x[u].x, y[u].x, eps);
+      const uint32_t k1 = key_from<MODE>(x[u].y, y[u].y, eps);
+      const uint32_t k2 = key_from<MODE>(x[u].z, y[u].z, eps);
+      const uint32_t k3 = key_from<MODE>(x[u].w, y[u].w, eps);
+      if ((k0 >> 16) == prefix) rc.push(bins, k0 & 0xffffu);
+      if ((k1 >> 16) == prefix) rc.push(bins, k1 & 0xffffu);
+      if ((k2 >> 16) == prefix) rc.push(bins, k2 & 0xffffu);
+      if ((k3 >> 16) == prefix) rc.push(bins, k3 & 0xffffu);
+    }
+  }
+  const int64_t tail0 = nvec << 2;
+  if (blockIdx.x == 0 && threadIdx.x < (n - tail0)) {
+    const int64_t i = tail0 + threadIdx.x;
+    const uint32_t k = key_from<MODE>(a[i], MODE == SFR_KEY_RATIO ? b[i] : 0.f, eps);
+    if ((k >> 16) == prefix) rc.push(bins, k & 0xffffu);
+  }
+  rc.flush(bins);
+}
+
+// ---- scans (one CTA) -----------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+
+// Finds the largest bin B with  above(B) < want <= above(B) + bins[B], scanning from the top.
+// Returns (B, above(B)) to every thread through shared memory; B = -1 if want > total.
+template <int NBINS>
+__device__ void find_bin_from_top(const unsigned long long* __restrict__ bins,
+                                  unsigned long long want, int* out_bin,
+                                  unsigned long long* out_above, unsigned long long* out_total) {
+  constexpr int kPer = NBINS / kScanThreads;
+  __shared__ unsigned long long part[kScanThreads];
+  __shared__ int s_bin;
+  __shared__ unsigned long long s_above;
+  // thread t owns the bins [hi - kPer + 1, hi] with hi = NBINS-1 - t*kPer (descending order)
+  const int hi = NBINS - 1 - (int)threadIdx.x * kPer;
+  unsigned long long mine = 0;
+#pragma unroll 4
+  for (int j = 0; j < kPer; ++j) mine += bins[hi - j];
+  part[threadIdx.x] = mine;
+  if (threadIdx.x == 0) {
+    s_bin = -1;
+    s_above = 0;
+  }
+  __syncthreads();
+  // inclusive scan over threads (Hillis-Steele; 1024 entries, 10 steps)
+  for (int off = 1; off < kScanThreads; off <<= 1) {
+    unsigned long long add = threadIdx.x >= off ? part[threadIdx.x - off] : 0ull;
+    __syncthreads();
+    part[threadIdx.x] += add;
+    __syncthreads();
+  }
+  const unsigned long long incl = part[threadIdx.x];
+  const unsigned long long excl = incl - mine;
+  if (want > excl && want <= incl) {  // exactly one thread
+    unsigned long long above = excl;
+    for (int j = 0; j < kPer; ++j) {
+      const unsigned long long c = bins[hi - j];
+      if (want <= above + c) {
+        s_bin = hi - j;
+        s_above = above;
+        break;
+      }
+      above += c;
+    }
+  }
+  __syncthreads();
+  *out_bin = s_bin;
+  *out_above = s_above;
+  *out_total = part[kScanThreads - 1];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kScanThreads, 1)
+select_scan_kernel(int pass, sfr_select_state* __restrict__ state,
+                   unsigned long long* __restrict__ bins) {
+  int bin;
+  unsigned long long above, total;
+  if (pass == 0) {
+    const unsigned long long k = state->k;
+    find_bin_from_top<SFR_SELECT_BINS0>(bins, k, &bin, &above, &total);
+    if (threadIdx.x == 0) {
+      state->select_none = (k == 0);
+      state->select_all = (k != 0 && bin < 0);  // k exceeds the element count
+      state->prefix = bin < 0 ? 0u : (uint32_t)bin;
+      state->k_in_bin = bin < 0 ? 0ull : k - above;
+      state->count_gt = above;  // completed by scan 1
+    }
+  } else {
+    if (state->select_none || state->select_all) {
+      bin = -1;
+      above = total = 0;
+    } else {
+      find_bin_from_top<SFR_SELECT_BINS1>(bins, state->k_in_bin, &bin, &above, &total);
+    }
+    if (threadIdx.x == 0 && bin >= 0) {
+      state->thr_key = (state->prefix << 16) | (uint32_t)bin;
+      state->count_gt += above;
+      state->count_eq = bins[bin];
+      state->tie_budget = state->k_in_bin - above;
+    }
+  }
+  __syncthreads();
+  // leave the bins clean for the next pass / the next select
+  for (int i = threadIdx.x; i < SFR_SELECT_BINS1; i += kScanThreads) bins[i] = 0ull;
+}
+
+// ---- apply -----------------------------------------------------------------------------------
+// Elements are cut into fixed chunks of kChunk consecutive elements; ordered ties need the
+// number of threshold-equal keys in all earlier chunks (scratch[chunk], exclusive).
+constexpr int kApplyThreads = 256;
+constexpr int kChunkVecs = 8;                            // float4 per thread per chunk
+constexpr int64_t kChunk = (int64_t)kApplyThreads * 4 * kChunkVecs;  // 8192 elements
+
+__device__ __forceinline__ bool ties_need_order(const sfr_select_state* s) {
+  return !s->select_none && !s->select_all && s->tie_budget != s->count_eq;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kApplyThreads, 4)
+select_tie_count_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps,
+                        int64_t n, const sfr_select_state* __restrict__ state,
+                        unsigned long long* __restrict__ scratch) {
+  if (!ties_need_order(state)) return;
+  __shared__ unsigned int red[32];
+  const uint32_t thr = state->thr_key;
+  const int64_t nchunks = (n + kChunk - 1) / kChunk;
+  for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int64_t base = c * kChunk;
+    unsigned int cnt = 0;
+    for (int j = 0; j < kChunkVecs * 4; ++j) {
+      const int64_t i = base + (int64_t)j * kApplyThreads + threadIdx.x;
+      if (i < n) cnt += key_from<MODE>(a[i], MODE == SFR_KEY_RATIO ? b[i] : 0.f, eps) == thr;
+    }
+    cnt = block_sum<unsigned int>(cnt, red);
+    if (threadIdx.x == 0) scratch[c] = cnt;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+select_tie_scan_kernel(int64_t nchunks, const sfr_select_state* __restrict__ state,
+                       const unsigned long long* __restrict__ tie_base,
+                       unsigned long long* __restrict__ scratch) {
+  if (!ties_need_order(state)) return;
+  __shared__ unsigned long long part[1024];
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = tie_base ? *tie_base : 0ull;
+  __syncthreads();
+  for (int64_t base = 0; base < nchunks; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const unsigned long long mine = i < nchunks ? scratch[i] : 0ull;
+    part[threadIdx.x] = mine;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      unsigned long long add = threadIdx.x >= off ? part[threadIdx.x - off] : 0ull;
+      __syncthreads();
+      part[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (i < nchunks) scratch[i] = carry + part[threadIdx.x] - mine;  // exclusive
+    __syncthreads();
+    if (threadIdx.x == 0) carry += part[1023];
+    __syncthreads();
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kApplyThreads, 4)
+select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps,
+                    int64_t n, const sfr_select_state* __restrict__ state,
+                    const unsigned long long* __restrict__ scratch, uint8_t* __restrict__ mask) {
+  __shared__ unsigned int warp_tot[kApplyThreads / 32];
+  __shared__ unsigned long long chunk_run;
+  const bool none = state->select_none != 0;
+  const bool all = state->select_all != 0;
+  const bool ordered = ties_need_order(state);
+  const uint32_t thr = state->thr_key;
+  const unsigned long long budget = state->tie_budget;
+  const int64_t nchunks = (n + kChunk - 1) / kChunk;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int64_t base = c * kChunk;
+    if (ordered) {
+      if (threadIdx.x == 0) chunk_run = scratch[c];
+      __syncthreads();
+    }
+    // a chunk is kChunkVecs slabs of kApplyThreads float4; thread t owns elements
+    // [slab*1024 + 4t, +4) so that flat order == (slab, thread, component) order
+    for (int sl = 0; sl < kChunkVecs; ++sl) {
+      const int64_t e0 = base + ((int64_t)sl * kApplyThreads + threadIdx.x) * 4;
+      uint32_t key[4];
+      bool valid[4];
+      if (e0 + 3 < n) {
+        const float4 x = ld_stream(reinterpret_cast<const float4*>(a + e0));
+        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (MODE == SFR_KEY_RATIO) y = ld_stream(reinterpret_cast<const float4*>(b + e0));
+        key[0] = key_from<MODE>(x.x, y.x, eps);
+        key[1] = key_from<MODE>(x.y, y.y, eps);
+        key[2] = key_from<MODE>(x.z, y.z, eps);
+        key[3] = key_from<MODE>(x.w, y.w, eps);
+        valid[0] = valid[1] = valid[2] = valid[3] = true;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          valid[q] = e0 + q < n;
+          key[q] = valid[q] ? key_from<MODE>(a[e0 + q], MODE == SFR_KEY_RATIO ? b[e0 + q] : 0.f, eps) : 0u;
+        }
+      }
+      uint32_t sel[4];
+      if (!ordered) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sel[q] = all ? 1u : (none ? 0u : (key[q] >= thr));
+      } else {
+        unsigned int tq[4], mine = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          tq[q] = valid[q] && key[q] == thr;
+          mine += tq[q];
+        }
+        // exclusive prefix of tie counts in flat order: warp scan, then across warps
+        unsigned int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int up = __shfl_up_sync(kFullMask, incl, o);
+          if (lane >= o) incl += up;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned int before = 0, slab_total = 0;
+#pragma unroll
+        for (int w = 0; w < kApplyThreads / 32; ++w) {
+          const unsigned int t = warp_tot[w];
+          if (w < warp) before += t;
+          slab_total += t;
+        }
+        unsigned long long rank = chunk_run + before + (incl - mine);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          sel[q] = key[q] > thr || (tq[q] && rank < budget);
+          rank += tq[q];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) chunk_run += slab_total;
+        __syncthreads();
+      }
+      if (e0 + 3 < n) {
+        __stcs(reinterpret_cast<unsigned int*>(mask + e0),
+               sel[0] | (sel[1] << 8) | (sel[2] << 16) | (sel[3] << 24));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (valid[q]) mask[e0 + q] = (uint8_t)sel[q];
+      }
+    }
+  }
+}
+
+__global__ void select_init_kernel(sfr_select_state* state, unsigned long long* bins,
+                                   unsigned long long k) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < SFR_SELECT_BINS1) bins[i] = 0ull;
+  if (i == 0) {
+    sfr_select_state z{};
+    z.k = k;
+    *state = z;
+  }
+}
+
+}  // namespace
+}  // namespace sfr
+
+extern "C" int sfr_select_init(sfr_select_state* state, unsigned long long* bins,
+                               unsigned long long k, sfr_stream_t stream) {
+  using namespace sfr;
+  SFR_REQUIRE_PTR(state);
+  SFR_REQUIRE_PTR(bins);
+  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  select_init_kernel<<<SFR_SELECT_BINS1 / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(state, bins, k);
+  SFR_LAUNCH_STATUS();
+}
+
+extern "C" int sfr_select_hist(const float* a, const float* b, int key_mode, float eps,
+                               int64_t n, int pass, const sfr_select_state* state,
+                               unsigned long long* bins, sfr_stream_t stream) {
+  using namespace sfr;
+  if (n < 0 || (pass != 0 && pass != 1)) return SFR_ERR_ARG;
+  if (key_mode != SFR_KEY_ABS && key_mode != SFR_KEY_RATIO) return SFR_ERR_ARG;
+  SFR_REQUIRE_PTR(bins);
+  SFR_REQUIRE_PTR(state);
+  if (n == 0) return SFR_OK;
+  SFR_REQUIRE_PTR(a);
+  if (key_mode == SFR_KEY_RATIO) SFR_REQUIRE_PTR(b);
+  SFR_REQUIRE_ALIGNED(a);
+  SFR_REQUIRE_ALIGNED(b);
+  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t nvec = n >> 2;
+  if (pass == 0) {
+    static bool attr_done = false;
+    const int smem = SFR_SELECT_BINS0 * (int)sizeof(unsigned int);
+    if (!attr_done) {
+      cudaFuncSetAttribute(select_hist0_kernel<SFR_KEY_ABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(select_hist0_kernel<SFR_KEY_RATIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attr_done = true;
+    }
+    const int64_t tile = (int64_t)kHistThreads * kHistUnroll;
+    const int grid = persistent_grid((nvec + tile - 1) / tile, 1);
+    if (key_mode == SFR_KEY_ABS) select_hist0_kernel<SFR_KEY_ABS><<<grid, kHistThreads, smem, s>>>(a, b, eps, n, bins);
+    else select_hist0_kernel<SFR_KEY_RATIO><<<grid, kHistThreads, smem, s>>>(a, b, eps, n, bins);
+  } else {
+    const int64_t tile = (int64_t)kFiltThreads * kFiltUnroll;
+    const int grid = persistent_grid((nvec + tile - 1) / tile, kFiltCtasPerSm);
+    if (key_mode == SFR_KEY_ABS) select_hist1_kernel<SFR_KEY_ABS><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins);
+    else select_hist1_kernel<SFR_KEY_RATIO><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins);
+  }
+  SFR_LAUNCH_STATUS();
+}
+
+extern "C" int sfr_select_scan(int pass, sfr_select_state* state, unsigned long long* bins,
+                               sfr_stream_t stream) {
+  using namespace sfr;
+  if (pass != 0 && pass != 1) return SFR_ERR_ARG;
+  SFR_REQUIRE_PTR(state);
+  SFR_REQUIRE_PTR(bins);
+  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  select_scan_kernel<<<1, kScanThreads, 0, static_cast<cudaStream_t>(stream)>>>(pass, state, bins);
+  SFR_LAUNCH_STATUS();
+}
+
+extern "C" int64_t sfr_select_scratch_elems(int64_t n) {
+  if (n <= 0) return 1;
+  return (n + sfr::kChunk - 1) / sfr::kChunk;
+}
+
+extern "C" int sfr_select_apply(const float* a, const float* b, int key_mode, float eps,
+                                int64_t n, const sfr_select_state* state,
+                                const unsigned long long* tie_base,
+                                unsigned long long* scratch, uint8_t* mask,
+                                sfr_stream_t stream) {
+  using namespace sfr;
+  if (n < 0) return SFR_ERR_ARG;
+  if (key_mode != SFR_KEY_ABS && key_mode != SFR_KEY_RATIO) return SFR_ERR_ARG;
+  SFR_REQUIRE_PTR(state);
+  if (n == 0) return SFR_OK;
+  SFR_REQUIRE_PTR(a);
+  if (key_mode == SFR_KEY_RATIO) SFR_REQUIRE_PTR(b);
+  SFR_REQUIRE_PTR(scratch);
+  SFR_REQUIRE_PTR(mask);
+  SFR_REQUIRE_ALIGNED(a);
+  SFR_REQUIRE_ALIGNED(b);
+  SFR_REQUIRE_ALIGNED(mask);
+  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t nchunks = (n + kChunk - 1) / kChunk;
+  const int grid = persistent_grid(nchunks, 8);
+  if (key_mode == SFR_KEY_ABS) {
+    select_tie_count_kernel<SFR_KEY_ABS><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch);
+    select_tie_scan_kernel<<<1, 1024, 0, s>>>(nchunks, state, tie_base, scratch);
+    select_apply_kernel<SFR_KEY_ABS><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch, mask);
+  } else {
+    select_tie_count_kernel<SFR_KEY_RATIO><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch);
+    select_tie_scan_kernel<<<1, 1024, 0, s>>>(nchunks, state, tie_base, scratch);
+    select_apply_kernel<SFR_KEY_RATIO><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch, mask);
+  }
+  SFR_LAUNCH_STATUS();
+}

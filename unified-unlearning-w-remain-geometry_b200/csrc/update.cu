@@ -1,0 +1,437 @@
+// update.cu — clip norm (masked sum of squares) and K3, the fused saliency-masked
+// fast/slow update of the SFR-on forget loops.
+//
+// Reference op sequence per forget iteration (one Python loop over named_parameters each):
+//   param.grad *= mask[name].to(device)      sfron.py:201-204, runners/diffusion.py:1126-1129,
+//                                            DiT/forget.py:289-292, SD gradient_ascent.py:94-99
+//   clip_grad_norm_(params, max_norm)        sfron.py:205, runners/diffusion.py:1131-1136,
+//                                            DiT/forget.py:293-298
+//   optimizer.step()                         SGD sfron.py:167-174,206,222 ; Adam
+//                                            runners/diffusion.py:1062,1138,1176 ; AdamW
+//                                            DiT/forget.py:199,299,320 ; Adam SD nsfw_removal.py:81,162,173
+//   EMA / slow weights                       DDPM/models/ema.py:17-24 ; DiT/forget.py:52-62 ;
+//                                            sfron.py:30-37,255-257
+// Here: one reduction pass (g, mask -> sum of squares) and ONE update pass that reads
+// g, mask, p, m, v (, ema) once and writes p, m, v (, ema, zeroed g, bf16 p) once.
+//
+// Arithmetic contract (torch 2.11 CPU kernels, probed op by op):
+//   add(b, alpha)   -> fma(b, alpha, a)          lerp(w<.5) -> fma(end-start, w, start)
+//   addcmul(value)  -> fma(value*t1, t2, self)   addcdiv    -> self + (value*t1)/t2   (no fma)
+//   mul / div / sqrt / add with a Python scalar -> the scalar rounded to fp32 first.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace sfr {
+namespace {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------ masked sum of squares
+constexpr int kSumsqCtasPerSm = 4;
+constexpr int kSumsqUnroll = 8;
+
+template <int GT, bool MASK>
+__global__ void __launch_bounds__(kThreads, kSumsqCtasPerSm)
+masked_sumsq_kernel(const void* __restrict__ g, const uint8_t* __restrict__ mask, int64_t n,
+                    double* __restrict__ out) {
+  __shared__ double scratch[32];
+  const int64_t nvec = n >> 2;
+  const int64_t tile = (int64_t)kThreads * kSumsqUnroll;
+  const int64_t ntiles = (nvec + tile - 1) / tile;
+  double total = 0.0;
+
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * tile + threadIdx.x;
+    float4 gg[kSumsqUnroll];
+    uint32_t mm[kSumsqUnroll];
+#pragma unroll
+    for (int u = 0; u < kSumsqUnroll; ++u) {
+      const int64_t v = base + (int64_t)u * kThreads;
+      const bool in = v < nvec;
+      gg[u] = in ? load_g4<GT>(g, v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (MASK) mm[u] = in ? load_mask4(mask, v) : 0u;
+    }
+    // fp32 partial over the 32 elements of this tile step, folded into a double per thread:
+    // the rounding error of the norm stays ~1e-8 relative for any n.
+    float part = 0.f;
+#pragma unroll
+    for (int u = 0; u < kSumsqUnroll; ++u) {
+      float x = gg[u].x, y = gg[u].y, z = gg[u].z, w = gg[u].w;
+      if constexpr (MASK) {
+        x = __fmul_rn(x, mask_byte_to_f32(mm[u], 0));
+        y = __fmul_rn(y, mask_byte_to_f32(mm[u], 1));
+        z = __fmul_rn(z, mask_byte_to_f32(mm[u], 2));
+        w = __fmul_rn(w, mask_byte_to_f32(mm[u], 3));
+      }
+      part = __fmaf_rn(x, x, part);
+      part = __fmaf_rn(y, y, part);
+      part = __fmaf_rn(z, z, part);
+      part = __fmaf_rn(w, w, part);
+    }
+    total += (double)part;
+  }
+
+  const int64_t tail0 = nvec << 2;
+  if (blockIdx.x == 0 && threadIdx.x < (n - tail0)) {
+    const int64_t i = tail0 + threadIdx.x;
+    float x = load_g1<GT>(g, i);
+    if constexpr (MASK) x = __fmul_rn(x, (float)mask[i]);
+    total += (double)x * (double)x;
+  }
+
+  total = block_sum<double>(total, scratch);
+  if (threadIdx.x == 0) atomicAdd(out, total);
+}
+
+// ------------------------------------------------------------------------- K3 constants
+struct UpdateConsts {
+  float neg_lr;         // SGD     : fp32(-lr)
+  float wd;             // SGD/Adam: fp32(weight_decay)      grad.add(param, alpha=wd)
+  float decay_mul;      // AdamW   : fp32(1 - lr*wd)         param.mul_(1 - lr*wd)
+  float lerp_w;         // Adam    : fp32(1 - beta1)         exp_avg.lerp_(grad, 1-beta1)
+  float beta2;          //           fp32(beta2)             exp_avg_sq.mul_(beta2)
+  float one_m_beta2;    //           fp32(1 - beta2)         .addcmul_(grad, grad, value=1-beta2)
+  float bc2_sqrt;       //           fp32((1 - beta2**t)**0.5)
+  float eps;            //           fp32(eps)
+  float neg_step_size;  //           fp32(-(lr / (1 - beta1**t)))
+  float momentum;       // SGD     : fp32(momentum)
+  float one_m_damp;     // SGD     : fp32(1 - dampening)
+  float ema_c1;         // mode-dependent, see ema_step
+  float ema_c2;
+  float max_norm;
+  uint32_t flags;
+  int has_wd;
+  int has_momentum;
+};
+
+// ---- slow / EMA weights ----------------------------------------------------------------
+// Returns the new slow value; may rewrite p (SLOWFAST).
+template <int EMA>
+__device__ __forceinline__ float ema_step(float& p, float s, const UpdateConsts& c) {
+  if constexpr (EMA == SFR_EMA_DDPM) {
+    // shadow = (1.0 - mu) * param + mu * shadow         DDPM/models/ema.py:22-24
+    return __fadd_rn(__fmul_rn(c.ema_c1, p), __fmul_rn(c.ema_c2, s));
+  } else if constexpr (EMA == SFR_EMA_DIT) {
+    // ema.mul_(decay).add_(param, alpha=1 - decay)      DiT/forget.py:62
+    return __fmaf_rn(p, c.ema_c2, __fmul_rn(s, c.ema_c1));
+  } else if constexpr (EMA == SFR_EMA_SLOWFAST) {
+    // p = (1 - beta) * p_prev + beta * p ; p_prev = copy(p)   sfron.py:126-127,30-37,255-257
+    p = __fadd_rn(__fmul_rn(c.ema_c1, s), __fmul_rn(c.ema_c2, p));
+    return p;
+  } else {
+    return s;
+  }
+}
+
+// ---- one parameter element ---------------------------------------------------------------
+template <int OPT>
+__device__ __forceinline__ void opt_step(float& p, float g, float& m, float& v,
+                                         const UpdateConsts& c) {
+  if constexpr (OPT == SFR_OPT_SGD) {
+    // torch/optim/sgd.py _single_tensor_sgd
+    if (c.has_wd) g = __fmaf_rn(p, c.wd, g);  // grad.add(param, alpha=wd)
+    if (c.has_momentum) {
+      if (c.flags & SFR_F_SGD_FIRST_STEP) {
+        m = g;  // buf = clone(grad)
+      } else {
+        m = __fmaf_rn(g, c.one_m_damp, __fmul_rn(m, c.momentum));  // buf.mul_(mom).add_(grad, alpha=1-damp)
+      }
+      g = m;
+    }
+    p = __fmaf_rn(g, c.neg_lr, p);  // param.add_(grad, alpha=-lr)
+  } else {
+    // torch/optim/adam.py _single_tensor_adam (capturable=False, amsgrad=False)
+    if (c.has_wd) {
+      if constexpr (OPT == SFR_OPT_ADAMW) {
+        p = __fmul_rn(p, c.decay_mul);  // param.mul_(1 - lr*wd)
+      } else {
+        g = __fmaf_rn(p, c.wd, g);  // grad.add(param, alpha=wd)
+      }
+    }
+    // exp_avg.lerp_(grad, w):  |w| < 0.5 ? fma(diff, w, start) : fma(diff, w-1, end)
+    const float diff = __fsub_rn(g, m);
+    m = fabsf(c.lerp_w) < 0.5f ? __fmaf_rn(diff, c.lerp_w, m)
+                               : __fmaf_rn(diff, __fsub_rn(c.lerp_w, 1.0f), g);
+    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+    v = __fmaf_rn(__fmul_rn(c.one_m_beta2, g), g, __fmul_rn(v, c.beta2));
+    // denom = (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), c.bc2_sqrt), c.eps);
+    // param.addcdiv_(exp_avg, denom, value=-step_size)
+    p = __fadd_rn(p, __fdiv_rn(__fmul_rn(c.neg_step_size, m), denom));
+  }
+}
+
+template <int OPT, int EMA>
+__device__ __forceinline__ void update_one(float& p, float g, float& m, float& v, float& s,
+                                           float maskf, float coef, const UpdateConsts& c) {
+  if (c.flags & SFR_F_MASK) g = __fmul_rn(g, maskf);              // param.grad *= mask
+  g = __fmul_rn(g, coef);                                           // clip: grad.mul_(coef)
+  if (c.flags & SFR_F_MASK_AFTER_CLIP) g = __fmul_rn(g, maskf);   // SalUn-DDPM order
+  opt_step<OPT>(p, g, m, v, c);
+  s = ema_step<EMA>(p, s, c);
+}
+
+constexpr int kUpdCtasPerSm = 3;
+
+template <int OPT, int EMA, int GT>
+__global__ void __launch_bounds__(kThreads, kUpdCtasPerSm)
+fused_update_kernel(float* __restrict__ p, void* __restrict__ g, float* __restrict__ m,
+                    float* __restrict__ v, const uint8_t* __restrict__ mask,
+                    float* __restrict__ ema, void* __restrict__ p_bf16, int64_t n,
+                    UpdateConsts c, const double* __restrict__ clip_sumsq) {
+  constexpr bool kHasV = OPT != SFR_OPT_SGD;
+  constexpr bool kHasEma = EMA != SFR_EMA_NONE;
+  const bool use_mask = (c.flags & (SFR_F_MASK | SFR_F_MASK_AFTER_CLIP)) != 0;
+  const bool has_m = kHasV || c.has_momentum;
+  const bool read_m = has_m && !(OPT == SFR_OPT_SGD && (c.flags & SFR_F_SGD_FIRST_STEP));
+  // coef == 1.0f exactly when not clipping: g * 1.0f is an exact no-op
+  const float coef = clip_sumsq ? clip_coef_from_sumsq(clip_sumsq, c.max_norm) : 1.0f;
+
+  const int64_t nvec = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  float4* e4 = reinterpret_cast<float4*>(ema);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int64_t vec = (int64_t)blockIdx.x * kThreads + threadIdx.x; vec < nvec;
+       vec += (int64_t)gridDim.x * kThreads) {
+    // issue every load of this step before the first use: 4-6 independent 128-bit
+    // requests in flight per thread
+    const float4 gg = load_g4<GT>(g, vec);
+    const uint32_t mk = use_mask ? load_mask4(mask, vec) : 0x01010101u;
+    float4 pp = ld_stream(p4 + vec);
+    float4 mm = read_m ? ld_stream(m4 + vec) : zero4;
+    float4 vv = kHasV ? ld_stream(v4 + vec) : zero4;
+    float4 ee = kHasEma ? ld_stream(e4 + vec) : zero4;
+
+    update_one<OPT, EMA>(pp.x, gg.x, mm.x, vv.x, ee.x, mask_byte_to_f32(mk, 0), coef, c);
+    update_one<OPT, EMA>(pp.y, gg.y, mm.y, vv.y, ee.y, mask_byte_to_f32(mk, 1), coef, c);
+    update_one<OPT, EMA>(pp.z, gg.z, mm.z, vv.z, ee.z, mask_byte_to_f32(mk, 2), coef, c);
+    update_one<OPT, EMA>(pp.w, gg.w, mm.w, vv.w, ee.w, mask_byte_to_f32(mk, 3), coef, c);
+
+    st_stream(p4 + vec, pp);
+    if (has_m) st_stream(m4 + vec, mm);
+    if constexpr (kHasV) st_stream(v4 + vec, vv);
+    if constexpr (kHasEma) st_stream(e4 + vec, ee);
+    if (c.flags & SFR_F_ZERO_GRAD) zero_g4<GT>(g, vec);
+    if (c.flags & SFR_F_WRITE_BF16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(pp.z, pp.w);
+      uint2 packed;
+      packed.x = *reinterpret_cast<uint32_t*>(&lo);
+      packed.y = *reinterpret_cast<uint32_t*>(&hi);
+      __stcs(reinterpret_cast<uint2*>(p_bf16) + vec, packed);
+    }
+  }
+
+  const int64_t tail0 = nvec << 2;
+  if (blockIdx.x == 0 && threadIdx.x < (n - tail0)) {
+    const int64_t i = tail0 + threadIdx.x;
+    float gg = load_g1<GT>(g, i);
+    float mk = use_mask ? (float)mask[i] : 1.0f;
+    float pp = p[i];
+    float mm = read_m ? m[i] : 0.f;
+    float vv = kHasV ? v[i] : 0.f;
+    float ee = kHasEma ? ema[i] : 0.f;
+    update_one<OPT, EMA>(pp, gg, mm, vv, ee, mk, coef, c);
+    p[i] = pp;
+    if (has_m) m[i] = mm;
+    if constexpr (kHasV) v[i] = vv;
+    if constexpr (kHasEma) ema[i] = ee;
+    if (c.flags & SFR_F_ZERO_GRAD) zero_g1<GT>(g, i);
+    if (c.flags & SFR_F_WRITE_BF16)
+      reinterpret_cast<__nv_bfloat16*>(p_bf16)[i] = __float2bfloat16_rn(pp);
+  }
+}
+
+// ------------------------------------------------------------------------- EMA alone
+template <int EMA>
+__global__ void __launch_bounds__(kThreads, 4)
+ema_only_kernel(const float* __restrict__ p, float* __restrict__ ema, int64_t n, UpdateConsts c) {
+  const int64_t nvec = n >> 2;
+  const float4* p4 = reinterpret_cast<const float4*>(p);
+  float4* e4 = reinterpret_cast<float4*>(ema);
+  for (int64_t vec = (int64_t)blockIdx.x * kThreads + threadIdx.x; vec < nvec;
+       vec += (int64_t)gridDim.x * kThreads) {
+    float4 pp = ld_stream(p4 + vec);
+    float4 ee = ld_stream(e4 + vec);
+    ee.x = ema_step<EMA>(pp.x, ee.x, c);
+    ee.y = ema_step<EMA>(pp.y, ee.y, c);
+    ee.z = ema_step<EMA>(pp.z, ee.z, c);
+    ee.w = ema_step<EMA>(pp.w, ee.w, c);
+    st_stream(e4 + vec, ee);
+  }
+  const int64_t tail0 = nvec << 2;
+  if (blockIdx.x == 0 && threadIdx.x < (n - tail0)) {
+    const int64_t i = tail0 + threadIdx.x;
+    float pp = p[i];
+    ema[i] = ema_step<EMA>(pp, ema[i], c);
+  }
+}
+
+void fill_ema_consts(UpdateConsts& c, int ema_mode, double a) {
+  // Python computes (1 - a) in double; torch rounds each scalar to fp32 when the op runs.
+  if (ema_mode == SFR_EMA_DDPM) {         // (1.0 - mu) * p + mu * s
+    c.ema_c1 = (float)(1.0 - a);
+    c.ema_c2 = (float)a;
+  } else if (ema_mode == SFR_EMA_DIT) {   // s.mul_(d).add_(p, alpha=1 - d)
+    c.ema_c1 = (float)a;
+    c.ema_c2 = (float)(1.0 - a);
+  } else if (ema_mode == SFR_EMA_SLOWFAST) {  // (1 - b) * prev + b * p
+    c.ema_c1 = (float)(1.0 - a);
+    c.ema_c2 = (float)a;
+  } else {
+    c.ema_c1 = c.ema_c2 = 0.f;
+  }
+}
+
+template <int OPT, int EMA>
+void launch_update_gt(int gt, int grid, cudaStream_t s, float* p, void* g, float* m, float* v,
+                      const uint8_t* mask, float* ema, void* p_bf16, int64_t n,
+                      const UpdateConsts& c, const double* clip_sumsq) {
+  if (gt == SFR_F32)
+    fused_update_kernel<OPT, EMA, SFR_F32><<<grid, kThreads, 0, s>>>(p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq);
+  else
+    fused_update_kernel<OPT, EMA, SFR_BF16><<<grid, kThreads, 0, s>>>(p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq);
+}
+
+template <int OPT>
+void launch_update_ema(int ema_mode, int gt, int grid, cudaStream_t s, float* p, void* g,
+                       float* m, float* v, const uint8_t* mask, float* ema, void* p_bf16,
+                       int64_t n, const UpdateConsts& c, const double* clip_sumsq) {
+  switch (ema_mode) {
+    case SFR_EMA_DDPM: launch_update_gt<OPT, SFR_EMA_DDPM>(gt, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq); break;
+    case SFR_EMA_DIT: launch_update_gt<OPT, SFR_EMA_DIT>(gt, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq); break;
+    case SFR_EMA_SLOWFAST: launch_update_gt<OPT, SFR_EMA_SLOWFAST>(gt, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq); break;
+    default: launch_update_gt<OPT, SFR_EMA_NONE>(gt, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq); break;
+  }
+}
+
+}  // namespace
+}  // namespace sfr
+
+extern "C" int sfr_masked_sumsq(const void* g, int g_dtype, const uint8_t* mask, int64_t n,
+                                double* out, sfr_stream_t stream) {
+  using namespace sfr;
+  if (n < 0) return SFR_ERR_ARG;
+  if (g_dtype != SFR_F32 && g_dtype != SFR_BF16) return SFR_ERR_ARG;
+  if (n == 0) return SFR_OK;
+  SFR_REQUIRE_PTR(g);
+  SFR_REQUIRE_PTR(out);
+  SFR_REQUIRE_ALIGNED(g);
+  SFR_REQUIRE_ALIGNED(mask);
+  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  const int64_t nvec = n >> 2;
+  const int64_t tile = (int64_t)kThreads * kSumsqUnroll;
+  const int grid = persistent_grid((nvec + tile - 1) / tile, kSumsqCtasPerSm);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (g_dtype == SFR_F32) {
+    if (mask) masked_sumsq_kernel<SFR_F32, true><<<grid, kThreads, 0, s>>>(g, mask, n, out);
+    else masked_sumsq_kernel<SFR_F32, false><<<grid, kThreads, 0, s>>>(g, mask, n, out);
+  } else {
+    if (mask) masked_sumsq_kernel<SFR_BF16, true><<<grid, kThreads, 0, s>>>(g, mask, n, out);
+    else masked_sumsq_kernel<SFR_BF16, false><<<grid, kThreads, 0, s>>>(g, mask, n, out);
+  }
+  SFR_LAUNCH_STATUS();
+}
+
+extern "C" int sfr_fused_update(float* p, void* g, float* m, float* v, const uint8_t* mask,
+                                float* ema, void* p_bf16, int64_t n,
+                                const sfr_update_args* a, const double* clip_sumsq,
+                                sfr_stream_t stream) {
+  using namespace sfr;
+  SFR_REQUIRE_PTR(a);
+  if (n < 0) return SFR_ERR_ARG;
+  if (a->opt < SFR_OPT_SGD || a->opt > SFR_OPT_ADAMW) return SFR_ERR_ARG;
+  if (a->ema_mode < SFR_EMA_NONE || a->ema_mode > SFR_EMA_SLOWFAST) return SFR_ERR_ARG;
+  if (a->g_dtype != SFR_F32 && a->g_dtype != SFR_BF16) return SFR_ERR_ARG;
+  const uint32_t known = SFR_F_MASK | SFR_F_MASK_AFTER_CLIP | SFR_F_ZERO_GRAD |
+                         SFR_F_SGD_FIRST_STEP | SFR_F_WRITE_BF16;
+  if (a->flags & ~known) return SFR_ERR_ARG;
+  if ((a->flags & SFR_F_MASK) && (a->flags & SFR_F_MASK_AFTER_CLIP)) return SFR_ERR_ARG;
+  if (a->opt != SFR_OPT_SGD && a->step < 1) return SFR_ERR_ARG;
+  if (n == 0) return SFR_OK;
+  const bool use_mask = (a->flags & (SFR_F_MASK | SFR_F_MASK_AFTER_CLIP)) != 0;
+  const bool has_momentum = a->opt == SFR_OPT_SGD && a->momentum != 0.0;
+  SFR_REQUIRE_PTR(p);
+  SFR_REQUIRE_PTR(g);
+  if (a->opt != SFR_OPT_SGD || has_momentum) SFR_REQUIRE_PTR(m);
+  if (a->opt != SFR_OPT_SGD) SFR_REQUIRE_PTR(v);
+  if (use_mask) SFR_REQUIRE_PTR(mask);
+  if (a->ema_mode != SFR_EMA_NONE) SFR_REQUIRE_PTR(ema);
+  if (a->flags & SFR_F_WRITE_BF16) SFR_REQUIRE_PTR(p_bf16);
+  SFR_REQUIRE_ALIGNED(p);
+  SFR_REQUIRE_ALIGNED(g);
+  SFR_REQUIRE_ALIGNED(m);
+  SFR_REQUIRE_ALIGNED(v);
+  SFR_REQUIRE_ALIGNED(mask);
+  SFR_REQUIRE_ALIGNED(ema);
+  SFR_REQUIRE_ALIGNED(p_bf16);
+  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+
+  // Scalars exactly as torch's Python forms them (double), rounded to fp32 where the
+  // ATen kernel would round them.
+  UpdateConsts c{};
+  c.flags = a->flags;
+  c.has_wd = a->weight_decay != 0.0;
+  c.has_momentum = has_momentum;
+  c.max_norm = (float)a->clip_max_norm;
+  c.wd = (float)a->weight_decay;
+  if (a->opt == SFR_OPT_SGD) {
+    c.neg_lr = (float)(-a->lr);
+    c.momentum = (float)a->momentum;
+    c.one_m_damp = (float)(1.0 - a->dampening);
+  } else {
+    const double step = (double)a->step;
+    const double bc1 = 1.0 - pow(a->beta1, step);        // 1 - beta1 ** step
+    const double bc2 = 1.0 - pow(a->beta2, step);        // 1 - beta2 ** step
+    const double step_size = a->lr / bc1;                // lr / bias_correction1
+    c.neg_step_size = (float)(-step_size);
+    c.bc2_sqrt = (float)pow(bc2, 0.5);                   // bias_correction2 ** 0.5
+    c.lerp_w = (float)(1.0 - a->beta1);
+    c.beta2 = (float)a->beta2;
+    c.one_m_beta2 = (float)(1.0 - a->beta2);
+    c.eps = (float)a->eps;
+    c.decay_mul = (float)(1.0 - a->lr * a->weight_decay);
+  }
+  fill_ema_consts(c, a->ema_mode, a->ema_a);
+
+  const int64_t nvec = n >> 2;
+  const int grid = persistent_grid((nvec + kThreads - 1) / kThreads, kUpdCtasPerSm * 8);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (a->opt) {
+    case SFR_OPT_SGD:
+      launch_update_ema<SFR_OPT_SGD>(a->ema_mode, a->g_dtype, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq);
+      break;
+    case SFR_OPT_ADAM:
+      launch_update_ema<SFR_OPT_ADAM>(a->ema_mode, a->g_dtype, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq);
+      break;
+    default:
+      launch_update_ema<SFR_OPT_ADAMW>(a->ema_mode, a->g_dtype, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq);
+      break;
+  }
+  SFR_LAUNCH_STATUS();
+}
+
+extern "C" int sfr_ema_update(const float* p, float* ema, int64_t n, int ema_mode, double ema_a,
+                              sfr_stream_t stream) {
+  using namespace sfr;
+  if (n < 0) return SFR_ERR_ARG;
+  if (ema_mode != SFR_EMA_DDPM && ema_mode != SFR_EMA_DIT) return SFR_ERR_ARG;
+  if (n == 0) return SFR_OK;
+  SFR_REQUIRE_PTR(p);
+  SFR_REQUIRE_PTR(ema);
+  SFR_REQUIRE_ALIGNED(p);
+  SFR_REQUIRE_ALIGNED(ema);
+  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  UpdateConsts c{};
+  fill_ema_consts(c, ema_mode, ema_a);
+  const int64_t nvec = n >> 2;
+  const int grid = persistent_grid((nvec + kThreads - 1) / kThreads, 32);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ema_mode == SFR_EMA_DDPM) ema_only_kernel<SFR_EMA_DDPM><<<grid, kThreads, 0, s>>>(p, ema, n, c);
+  else ema_only_kernel<SFR_EMA_DIT><<<grid, kThreads, 0, s>>>(p, ema, n, c);
+  SFR_LAUNCH_STATUS();
+}

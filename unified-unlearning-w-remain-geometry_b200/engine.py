@@ -1,0 +1,253 @@
+"""Host side of the SFR-on hot path over flat device vectors.
+
+`HotPath` owns the per-role flat buffers of ONE shard (Fisher accumulators, mask, optimizer
+state, slow/EMA weights) and sequences the C-ABI kernels in the order the reference's loops
+do their torch ops.  It holds no model: callers hand it the flat weight / gradient vectors
+(`FlatParams.p`, `.g`, or any 16-byte-aligned slices of them when sharded).
+
+Reference order of operations:
+  Fisher    F += grad**2 / L                     per batch          -> fisher_accumulate()
+  mask      (F_f+1e-15)/(F_r+1e-15) >= th        once per threshold -> ratio_mask()
+            top-k of |sum grad|                  SalUn              -> topk_mask()
+  forget    grad *= mask ; clip ; optimizer.step                    -> forget_step()
+  remain    [clip ;] optimizer.step ; EMA / slow-fast               -> remain_step()
+One optimizer state serves both steps (`step` advances twice per iteration), exactly as the
+single torch optimizer object of every reference loop.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import capi
+
+
+@dataclass
+class OptConfig:
+    """Hyper-parameters of the optimizer the reference constructs.
+
+    kind: "sgd" (sfron.py:167-170), "adam" (DDPM/functions/__init__.py:9-18, SD nsfw_removal.py:81),
+    "adamw" (DiT/forget.py:199)."""
+    kind: str = "adamw"
+    lr: float = 1e-4
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+    weight_decay: float = 0.0
+    momentum: float = 0.0
+    dampening: float = 0.0
+
+    def code(self) -> int:
+        return {"sgd": capi.OPT_SGD, "adam": capi.OPT_ADAM, "adamw": capi.OPT_ADAMW}[self.kind]
+
+
+_EMA_CODES = {"none": capi.EMA_NONE, "ddpm": capi.EMA_DDPM, "dit": capi.EMA_DIT, "slowfast": capi.EMA_SLOWFAST}
+
+
+class HotPath:
+    def __init__(self, n: int, device, opt: OptConfig, *, ema_mode: str = "none", ema_a: float = 0.0,
+                 grad_dtype: torch.dtype = torch.float32):
+        self.n = int(n)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise capi.SfrError(capi.ERR_NO_DEVICE, "HotPath", "the SFR-on hot path runs on CUDA only")
+        capi.load()
+        self.opt = opt
+        self.ema_mode = ema_mode
+        self.ema_a = float(ema_a)
+        self.grad_dtype = grad_dtype
+        self.step_count = 0            # torch optimizer state['step'] (shared by forget and remain)
+        self._buf: Dict[str, torch.Tensor] = {}
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.zero_count = torch.zeros(capi.MAX_THRESHOLDS, dtype=torch.int64, device=self.device)
+        self._select = None
+
+    # ---- lazily allocated role buffers ------------------------------------------------------------
+    def buffer(self, role: str, dtype=torch.float32) -> torch.Tensor:
+        t = self._buf.get(role)
+        if t is None:
+            t = torch.zeros(self.n, dtype=dtype, device=self.device)
+            self._buf[role] = t
+        return t
+
+    def has(self, role: str) -> bool:
+        return role in self._buf
+
+    def set_buffer(self, role: str, t: torch.Tensor) -> None:
+        if t.numel() != self.n or t.device != self.device:
+            raise ValueError(f"buffer {role}: wrong size or device")
+        self._buf[role] = t.contiguous()
+
+    @property
+    def forget_fisher(self) -> torch.Tensor:
+        return self.buffer("forget_fisher")
+
+    @property
+    def remain_fisher(self) -> torch.Tensor:
+        return self.buffer("remain_fisher")
+
+    @property
+    def mask(self) -> torch.Tensor:
+        return self.buffer("mask", torch.uint8)
+
+    @property
+    def m(self) -> torch.Tensor:
+        return self.buffer("m")
+
+    @property
+    def v(self) -> torch.Tensor:
+        return self.buffer("v")
+
+    @property
+    def slow(self) -> torch.Tensor:
+        return self.buffer("slow")
+
+    def init_slow(self, p: torch.Tensor) -> None:
+        """EMAHelper.register / `ema = deepcopy(model)` / `ori_model = deepcopy(model)`:
+        the slow weights start as a copy of the weights."""
+        self.buffer("slow").copy_(p)
+
+    # ---- K1 ---------------------------------------------------------------------------------------
+    def fisher_accumulate(self, which: str, g: torch.Tensor, divisor: float, *,
+                          clip_max_norm: Optional[float] = None) -> None:
+        """`F[which] += g**2 / divisor`; with `clip_max_norm` the gradient is clipped first, as in
+        DDPM/runners/diffusion.py:1270-1281."""
+        acc = self.buffer({"forget": "forget_fisher", "remain": "remain_fisher"}.get(which, which))
+        if clip_max_norm is None:
+            capi.fisher_accum(acc, g, divisor)
+        else:
+            self.sumsq.zero_()
+            capi.masked_sumsq(g if g.dim() == 1 else g.reshape(-1), None, self.sumsq)
+            self.reduce_scalar_(self.sumsq)
+            capi.fisher_accum(acc, g, divisor, clip_sumsq=self.sumsq, clip_max_norm=clip_max_norm)
+
+    # ---- K2a --------------------------------------------------------------------------------------
+    def ratio_mask(self, threshold: float, *, eps: float = 1e-15, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Writes the bool mask (uint8 storage) and leaves the zero count in `self.zero_count[0]`."""
+        mask = self.mask if out is None else out
+        self.zero_count.zero_()
+        capi.ratio_mask(self.forget_fisher, self.remain_fisher, threshold, mask, self.zero_count, eps)
+        return mask
+
+    def ratio_masks(self, thresholds: Sequence[float], *, eps: float = 1e-15) -> torch.Tensor:
+        """All thresholds in one pass over the two Fisher vectors -> [T, stride] uint8."""
+        stride = (self.n + 15) // 16 * 16
+        masks = torch.empty(len(thresholds), stride, dtype=torch.uint8, device=self.device)
+        self.zero_count.zero_()
+        capi.ratio_mask_multi(self.forget_fisher, self.remain_fisher, thresholds, masks, self.zero_count, eps)
+        return masks
+
+    # ---- K2b --------------------------------------------------------------------------------------
+    def _select_buffers(self):
+        if self._select is None:
+            state = torch.zeros(capi.SELECT_STATE_BYTES // 8, dtype=torch.int64, device=self.device)
+            bins = torch.zeros(capi.SELECT_BINS1, dtype=torch.int64, device=self.device)
+            scratch = torch.zeros(capi.select_scratch_elems(self.n), dtype=torch.int64, device=self.device)
+            self._select = (state, bins, scratch)
+        return self._select
+
+    def topk_mask(self, values: torch.Tensor, k: int, *, other: Optional[torch.Tensor] = None,
+                  eps: float = 1e-15, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Exact global top-k of |values| (or of the ratio (values+eps)/(other+eps)); ties at the
+        threshold go to the lowest flat index.  `k` is the GLOBAL count across shards."""
+        mode = capi.KEY_ABS if other is None else capi.KEY_RATIO
+        state, bins, scratch = self._select_buffers()
+        mask = self.mask if out is None else out
+        capi.select_init(state, bins, k)
+        capi.select_hist(values, other, mode, 0, state, bins, eps)
+        self.reduce_bins_(bins, capi.SELECT_BINS0)
+        capi.select_scan(0, state, bins)
+        capi.select_hist(values, other, mode, 1, state, bins, eps)
+        local_bins = self.keep_local_bins_(bins)
+        self.reduce_bins_(bins, capi.SELECT_BINS1)
+        capi.select_scan(1, state, bins)
+        tie_base = self.tie_base_(state, local_bins)
+        capi.select_apply(values, other, mode, state, tie_base, scratch, mask, eps)
+        return mask
+
+    def select_state(self) -> capi.SelectState:
+        return capi.read_select_state(self._select_buffers()[0])
+
+    # ---- collectives: identity on one GPU, overridden by dist.ShardedHotPath --------------------------
+    def reduce_scalar_(self, t: torch.Tensor) -> None:
+        pass
+
+    def reduce_bins_(self, bins: torch.Tensor, count: int) -> None:
+        pass
+
+    def keep_local_bins_(self, bins: torch.Tensor) -> Optional[torch.Tensor]:
+        return None
+
+    def tie_base_(self, state: torch.Tensor, local_bins: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        return None
+
+    # ---- clip norm + K3 ---------------------------------------------------------------------------
+    def _args(self, flags: int, ema: bool, max_norm: Optional[float], lr: Optional[float]) -> capi.UpdateArgs:
+        o = self.opt
+        a = capi.UpdateArgs()
+        a.opt = o.code()
+        a.ema_mode = _EMA_CODES[self.ema_mode] if ema else capi.EMA_NONE
+        a.flags = flags
+        a.step = self.step_count
+        a.lr = o.lr if lr is None else lr
+        a.beta1, a.beta2, a.eps = o.beta1, o.beta2, o.eps
+        a.weight_decay, a.momentum, a.dampening = o.weight_decay, o.momentum, o.dampening
+        a.ema_a = self.ema_a
+        a.clip_max_norm = 0.0 if max_norm is None else max_norm
+        return a
+
+    def _step(self, p: torch.Tensor, g: torch.Tensor, *, mask: Optional[torch.Tensor], mask_order: str,
+              max_norm: Optional[float], ema: bool, lr: Optional[float], zero_grad: bool,
+              p_bf16: Optional[torch.Tensor]) -> None:
+        flags = 0
+        if mask is not None:
+            flags |= capi.F_MASK if mask_order == "mask_then_clip" else capi.F_MASK_AFTER_CLIP
+        if zero_grad:
+            flags |= capi.F_ZERO_GRAD
+        if p_bf16 is not None:
+            flags |= capi.F_WRITE_BF16
+        sgd = self.opt.kind == "sgd"
+        if sgd and self.opt.momentum != 0.0 and not self.has("m"):
+            flags |= capi.F_SGD_FIRST_STEP      # torch creates momentum_buffer = clone(grad) on first use
+        clip = None
+        if max_norm is not None:
+            # norm of the gradient as clip_grad_norm_ sees it: masked already (SFR-on order) or raw
+            self.sumsq.zero_()
+            capi.masked_sumsq(g, mask if (mask is not None and mask_order == "mask_then_clip") else None, self.sumsq)
+            self.reduce_scalar_(self.sumsq)
+            clip = self.sumsq
+        self.step_count += 1
+        a = self._args(flags, ema, max_norm, lr)
+        use_ema = ema and self.ema_mode != "none"
+        capi.fused_update(p, g, None if (sgd and self.opt.momentum == 0.0) else self.m,
+                          None if sgd else self.v, mask, self.slow if use_ema else None, a,
+                          clip_sumsq=clip, p_bf16=p_bf16)
+
+    def forget_step(self, p: torch.Tensor, g: torch.Tensor, *, mask: Optional[torch.Tensor] = None,
+                    use_mask: bool = True, max_norm: Optional[float] = None, lr: Optional[float] = None,
+                    mask_order: str = "mask_then_clip", zero_grad: bool = False,
+                    p_bf16: Optional[torch.Tensor] = None) -> None:
+        """grad *= mask ; clip_grad_norm_(max_norm) ; optimizer.step()
+        (sfron.py:201-206; runners/diffusion.py:1126-1138; DiT/forget.py:289-299)."""
+        if mask is None and use_mask:
+            mask = self.mask
+        self._step(p, g, mask=mask if use_mask else None, mask_order=mask_order, max_norm=max_norm,
+                   ema=False, lr=lr, zero_grad=zero_grad, p_bf16=p_bf16)
+
+    def remain_step(self, p: torch.Tensor, g: torch.Tensor, *, max_norm: Optional[float] = None,
+                    lr: Optional[float] = None, ema: bool = True, zero_grad: bool = False,
+                    p_bf16: Optional[torch.Tensor] = None) -> None:
+        """[clip ;] optimizer.step() ; EMA / slow-fast update
+        (sfron.py:213-222,255-257; runners/diffusion.py:1156-1180; DiT/forget.py:310-322)."""
+        self._step(p, g, mask=None, mask_order="mask_then_clip", max_norm=max_norm, ema=ema, lr=lr,
+                   zero_grad=zero_grad, p_bf16=p_bf16)
+
+    def grad_norm(self) -> torch.Tensor:
+        """Total norm of the last clipped step (what clip_grad_norm_ returns), fp32 device scalar."""
+        return self.sumsq.sqrt().float()
+
+    def ema_only(self, p: torch.Tensor, slow: torch.Tensor) -> None:
+        """EMA of parameters the optimizer never touches (frozen DiT pos_embed, DiT/forget.py:58-62)."""
+        capi.ema_update(p, slow, _EMA_CODES[self.ema_mode], self.ema_a)

@@ -1,0 +1,195 @@
+"""Flat parameter-vector layout: the HBM data layout of the SFR-on hot path.
+
+The reference walks `model.named_parameters()` in Python for every stage (Fisher, mask,
+mask-apply, clip, step, EMA: SURVEY.md §3.5).  Here every role of the path — weights `p`,
+gradients `g`, optimizer state `m`/`v`, slow/EMA weights, the two Fisher accumulators and the
+saliency mask — is ONE contiguous device buffer over the same element order, so each stage is
+one kernel launch over `n` elements.
+
+Order and packing: trainable parameters (those with requires_grad) in `named_parameters()`
+order, TIGHTLY packed — flat index == index in the reference's
+`torch.cat([t.flatten() for t in gradients.values()])` (DDPM/runners/diffusion.py:1009-1012),
+which is what makes top-k tie-breaking by lowest flat index equal to a stable argsort of the
+reference's vector.  There is no per-tensor padding, hence nothing to exclude from norms, counts
+or top-k.  Tensor starts are 16-byte aligned whenever all preceding sizes are multiples of 4,
+which holds for every tensor of the four reference models except a trailing 3- or 10-element
+bias (verified by instantiating them).  Frozen parameters (DiT `pos_embed`) are kept
+in a separate small segment list: only the reference's EMA loop touches them.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import torch
+
+
+@dataclass(frozen=True)
+class Segment:
+    name: str
+    shape: Tuple[int, ...]
+    offset: int
+    numel: int
+
+
+class FlatLayout:
+    """Name <-> offset table of a flat vector.  Pure host logic (no device, no kernels)."""
+
+    def __init__(self, named_shapes: Iterable[Tuple[str, Sequence[int]]]):
+        self.segments: List[Segment] = []
+        off = 0
+        for name, shape in named_shapes:
+            shape = tuple(int(s) for s in shape)
+            numel = 1
+            for s in shape:
+                numel *= s
+            self.segments.append(Segment(name, shape, off, numel))
+            off += numel
+        self.numel = off
+        self._by_name = {s.name: s for s in self.segments}
+        if len(self._by_name) != len(self.segments):
+            raise ValueError("duplicate parameter names in layout")
+
+    @classmethod
+    def from_named_tensors(cls, named: Iterable[Tuple[str, torch.Tensor]]) -> "FlatLayout":
+        return cls((n, tuple(t.shape)) for n, t in named)
+
+    def __len__(self) -> int:
+        return len(self.segments)
+
+    def __iter__(self) -> Iterator[Segment]:
+        return iter(self.segments)
+
+    def __contains__(self, name: str) -> bool:
+        return name in self._by_name
+
+    def segment(self, name: str) -> Segment:
+        return self._by_name[name]
+
+    @property
+    def names(self) -> List[str]:
+        return [s.name for s in self.segments]
+
+    def misaligned(self, multiple: int = 4) -> List[Segment]:
+        """Segments whose start is not a multiple of `multiple` elements (16 B for fp32)."""
+        return [s for s in self.segments if s.offset % multiple]
+
+    def view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        s = self._by_name[name]
+        return flat[s.offset:s.offset + s.numel].view(s.shape)
+
+    def views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        if flat.numel() != self.numel:
+            raise ValueError(f"flat vector has {flat.numel()} elements, layout has {self.numel}")
+        return {s.name: flat[s.offset:s.offset + s.numel].view(s.shape) for s in self.segments}
+
+    def flatten(self, tensors: Dict[str, torch.Tensor], *, dtype=None, device=None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Pack a name->tensor dict into one flat vector (missing names are an error)."""
+        if out is None:
+            first = tensors[self.segments[0].name] if self.segments else torch.empty(0)
+            out = torch.empty(self.numel, dtype=dtype or first.dtype, device=device or first.device)
+        for s in self.segments:
+            out[s.offset:s.offset + s.numel].copy_(tensors[s.name].reshape(-1))
+        return out
+
+    # ---- shard partition (multi-GPU) --------------------------------------------------------
+    def shard_bounds(self, world: int, rank: int, align: int = 16) -> Tuple[int, int]:
+        return shard_bounds(self.numel, world, rank, align)
+
+
+def shard_bounds(n: int, world: int, rank: int, align: int = 16) -> Tuple[int, int]:
+    """Contiguous, `align`-element-aligned shard [lo, hi) of an n-element vector.
+
+    Every shard start is a multiple of `align` elements (default 16: 16 bytes even for the
+    1-byte mask stream) so the kernels' 128-bit accesses stay aligned; shard sizes differ by at
+    most `align`; the ragged end (n % align) lands in the last non-empty shard.  No padding elements exist: shards
+    partition [0, n) exactly, so norms / counts / top-k need no exclusion logic.
+    """
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    units = (n + align - 1) // align
+    per, extra = divmod(units, world)
+    lo_u = rank * per + min(rank, extra)
+    hi_u = lo_u + per + (1 if rank < extra else 0)
+    return min(lo_u * align, n), min(hi_u * align, n)
+
+
+class FlatParams:
+    """Device buffers of the hot path for one model, with per-name views.
+
+    `adopt(model)` re-points every trainable `param.data` (and optionally `param.grad`) into the
+    flat `p` (`g`) buffer, so autograd reads weights from and accumulates gradients into the
+    flat vectors directly: no gather before, no scatter after the kernels.
+    """
+
+    def __init__(self, model: torch.nn.Module, device=None, *, grads_as_views: bool = True,
+                 grad_dtype: torch.dtype = torch.float32):
+        named = list(model.named_parameters())
+        train = [(n, p) for n, p in named if p.requires_grad]
+        frozen = [(n, p) for n, p in named if not p.requires_grad]
+        self.all_names = [n for n, _ in named]
+        self.layout = FlatLayout.from_named_tensors(train)
+        self.frozen_layout = FlatLayout.from_named_tensors(frozen)
+        if device is None:
+            device = train[0][1].device if train else torch.device("cuda")
+        self.device = torch.device(device)
+        n = self.layout.numel
+        self.n = n
+        self.p = torch.empty(n, dtype=torch.float32, device=self.device)
+        self.g = torch.zeros(n, dtype=grad_dtype, device=self.device)
+        self.frozen = torch.empty(self.frozen_layout.numel, dtype=torch.float32, device=self.device)
+        with torch.no_grad():
+            for seg, (_, prm) in zip(self.layout, train):
+                self.p[seg.offset:seg.offset + seg.numel].copy_(prm.detach().reshape(-1))
+                prm.data = self.p[seg.offset:seg.offset + seg.numel].view(seg.shape)
+                if grads_as_views and grad_dtype == torch.float32:
+                    prm.grad = self.g[seg.offset:seg.offset + seg.numel].view(seg.shape)
+            for seg, (_, prm) in zip(self.frozen_layout, frozen):
+                self.frozen[seg.offset:seg.offset + seg.numel].copy_(prm.detach().reshape(-1))
+                prm.data = self.frozen[seg.offset:seg.offset + seg.numel].view(seg.shape)
+        self.grads_as_views = grads_as_views and grad_dtype == torch.float32
+        self._train_params = [p for _, p in train]
+        self._gather_tables = None
+
+    # ---- buffers of the other roles, allocated on demand ------------------------------------
+    def new_buffer(self, dtype=torch.float32, zero: bool = True) -> torch.Tensor:
+        f = torch.zeros if zero else torch.empty
+        return f(self.n, dtype=dtype, device=self.device)
+
+    def zero_grad(self) -> None:
+        """One memset instead of optimizer.zero_grad()'s per-tensor loop.  (The fused update can
+        also zero `g` on its way out: SFR_F_ZERO_GRAD.)"""
+        self.g.zero_()
+
+    def collect_grads(self) -> torch.Tensor:
+        """Make sure `g` holds this step's gradients.  With view-grads this is free; otherwise
+        the per-tensor `.grad` tensors autograd allocated are gathered by ONE kernel."""
+        if self.grads_as_views:
+            return self.g
+        from . import capi
+        srcs, sizes, dt = [], [], None
+        for seg, prm in zip(self.layout, self._train_params):
+            if prm.grad is None:
+                raise RuntimeError(f"parameter {seg.name} has no gradient")
+            gt = prm.grad
+            if not gt.is_contiguous():
+                gt = gt.contiguous()
+            dt = gt.dtype if dt is None else dt
+            if gt.dtype != dt:
+                raise RuntimeError("mixed gradient dtypes")
+            srcs.append(gt.data_ptr())
+            sizes.append(seg.numel)
+        if self._gather_tables is None:
+            offs = torch.tensor([s.offset for s in self.layout], dtype=torch.int64)
+            self._gather_tables = (offs.to(self.device), torch.tensor(sizes, dtype=torch.int64).to(self.device))
+        offs_d, sizes_d = self._gather_tables
+        srcs_d = torch.tensor(srcs, dtype=torch.int64).to(self.device, non_blocking=False)
+        if self.g.dtype != torch.float32:
+            self.g = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        capi.gather_segments(self.g, srcs_d, offs_d, sizes_d,
+                             capi.F32 if dt == torch.float32 else capi.BF16, self.n)
+        return self.g
+
+    def named_views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return self.layout.views(flat)
