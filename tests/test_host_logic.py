@@ -1,0 +1,143 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what include/sfron_b200.h declares,
+flat layout / shard arithmetic, reference file formats, and the no-fallback guarantees."""
+import os
+import re
+
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st
+
+from conftest import ROOT, load_golden
+
+import sfron_b200 as sfr
+from sfron_b200 import capi, formats
+from sfron_b200.dist import scan_from_top, tie_bases
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "sfron_b200.h")).read()
+    declared = set(re.findall(r"^SFR_API [\w\s\*]+?\b(sfr_\w+)\(", header, flags=re.M))
+    assert declared == set(capi.EXPORTED_SYMBOLS), declared ^ set(capi.EXPORTED_SYMBOLS)
+    lib = capi.load()
+    for sym in declared:
+        assert hasattr(lib, sym)
+    assert lib.sfr_abi_version() == capi.ABI_VERSION
+    assert b"no CPU fallback" in lib.sfr_error_string(capi.ERR_NO_DEVICE)
+
+
+def test_update_args_struct_matches_header():
+    header = open(os.path.join(ROOT, "include", "sfron_b200.h")).read()
+    body = re.search(r"typedef struct sfr_update_args \{(.*?)\} sfr_update_args;", header, flags=re.S).group(1)
+    fields = re.findall(r"^\s*(?:int32_t|uint32_t|int64_t|double)\s+(\w+);", body, flags=re.M)
+    assert fields == [f[0] for f in capi.UpdateArgs._fields_]
+    body = re.search(r"typedef struct sfr_select_state \{(.*?)\} sfr_select_state;", header, flags=re.S).group(1)
+    fields = re.findall(r"^\s*(?:unsigned long long|uint32_t)\s+(\w+)", body, flags=re.M)
+    assert fields == [f[0] for f in capi.SelectState._fields_]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour WITHOUT a GPU")
+def test_no_cpu_fallback_anywhere():
+    with pytest.raises(capi.SfrError) as e:
+        capi.device_info()
+    assert e.value.code == capi.ERR_NO_DEVICE
+    with pytest.raises(capi.SfrError):
+        sfr.HotPath(16, "cpu", sfr.OptConfig())
+    with pytest.raises(capi.SfrError):
+        capi.fisher_accum(torch.zeros(16), torch.zeros(16), 1.0)
+    with pytest.raises(capi.SfrError):
+        capi.masked_sumsq(torch.zeros(16), None, torch.zeros(1, dtype=torch.float64))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "unified-unlearning-w-remain-geometry_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_flat_layout_offsets_and_views():
+    L = sfr.FlatLayout([("a.weight", (3, 4)), ("a.bias", (4,)), ("s", ()), ("b", (2, 2, 2))])
+    assert L.numel == 12 + 4 + 1 + 8 and L.names == ["a.weight", "a.bias", "s", "b"]
+    assert [s.offset for s in L] == [0, 12, 16, 17]
+    assert [s.name for s in L.misaligned(4)] == ["b"]
+    flat = torch.arange(L.numel, dtype=torch.float32)
+    v = L.views(flat)
+    assert v["a.bias"].tolist() == [12, 13, 14, 15] and v["s"].shape == () and v["b"].shape == (2, 2, 2)
+    assert torch.equal(L.flatten(v), flat)
+    v["s"].fill_(-1)                                  # views alias the flat vector
+    assert flat[16] == -1
+    with pytest.raises(ValueError):
+        sfr.FlatLayout([("x", (1,)), ("x", (2,))])
+
+
+@settings(max_examples=200, deadline=None)
+@given(n=st.integers(0, 10_000_000), world=st.integers(1, 16), align=st.sampled_from([1, 4, 16]))
+def test_shard_bounds_partition(n, world, align):
+    bounds = [sfr.shard_bounds(n, world, r, align) for r in range(world)]
+    assert bounds[0][0] == 0 and bounds[-1][1] == n
+    for (lo, hi), (lo2, _) in zip(bounds, bounds[1:]):
+        assert hi == lo2 and lo <= hi
+    for lo, hi in bounds:
+        assert lo % align == 0 or lo == n
+    sizes = [hi - lo for lo, hi in bounds]
+    assert max(sizes) - min(sizes) < 2 * align      # one unit, plus the ragged last unit
+
+
+def test_formats_round_trip_reference_files(tmp_path):
+    fx = load_golden("dit_ratio_mask.pt")
+    all_names = list(fx["forget"].keys())
+    layout = sfr.FlatLayout([(n, tuple(t.shape)) for n, t in fx["forget"].items() if torch.is_tensor(t)])
+    ff = formats.dict_to_flat(layout, fx["forget"])
+    back = formats.flat_to_dict(layout, ff, all_names=all_names)
+    assert list(back.keys()) == all_names
+    for n in all_names:
+        if torch.is_tensor(fx["forget"][n]):
+            assert torch.equal(back[n], fx["forget"][n]) and back[n].dtype == torch.float32
+        else:
+            assert back[n] == 0 and isinstance(back[n], int)            # pos_embed placeholder survives
+    # files written by us load like the reference's own
+    formats.save_fisher(tmp_path / "forget_fisher.pt", layout, ff, all_names=all_names)
+    again = torch.load(tmp_path / "forget_fisher.pt", weights_only=False)
+    assert all(torch.equal(again[n], fx["forget"][n]) for n in layout.names)
+    ref_mask = fx["masks"]["1"]
+    flat_mask = formats.load_mask(ref_mask, layout)
+    assert flat_mask.dtype == torch.uint8
+    d = formats.ratio_mask_to_dict(layout, flat_mask, all_names=all_names)
+    assert all(d[n].dtype == torch.bool and torch.equal(d[n], ref_mask[n]) for n in layout.names)
+    d64 = formats.topk_mask_to_dict(layout, flat_mask)
+    assert all(v.dtype == torch.int64 for v in d64.values())
+    assert formats.threshold_tag(1.0) == "1.0" and formats.threshold_tag(1) == "1"
+    with pytest.raises(ValueError):
+        formats.dict_to_flat(sfr.FlatLayout([("module.pos_embed", (1, 6, 8))]), fx["forget"])
+
+
+def test_adam_state_dict_loads_into_torch_optimizer():
+    model = torch.nn.Linear(5, 3)
+    layout = sfr.FlatLayout.from_named_tensors(model.named_parameters())
+    m = torch.randn(layout.numel)
+    v = torch.rand(layout.numel)
+    sd = formats.adam_state_dict(layout, m, v, 7, lr=1e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt.load_state_dict(sd)
+    st0 = opt.state[model.weight]
+    assert torch.equal(st0["exp_avg"].reshape(-1), m[:15]) and float(st0["step"]) == 7
+    m2, v2, step = formats.load_adam_state(layout, opt.state_dict())
+    assert torch.equal(m2, m) and torch.equal(v2, v) and step == 7
+
+
+@settings(max_examples=100, deadline=None)
+@given(data=st.data())
+def test_scan_from_top_matches_bruteforce(data):
+    nb = data.draw(st.sampled_from([4, 64, 1024]))
+    counts = data.draw(st.lists(st.integers(0, 5), min_size=nb, max_size=nb))
+    bins = torch.tensor(counts, dtype=torch.int64)
+    total = int(bins.sum())
+    want = data.draw(st.integers(0, total + 2))
+    b, above = scan_from_top(bins, want)
+    if want == 0 or want > total:
+        assert b == -1
+    else:
+        assert above < want <= above + counts[b] and above == sum(counts[b + 1:])
+    assert tie_bases([3, 0, 2]) == [0, 3, 3]

@@ -50,7 +50,6 @@ def test_salun_topk_mask():
     names, shapes = fx["names"], fx["shapes"]
     for th in ("0.2", "0.5"):
         rec = fx[th]
-        acc = rec["grads"].sum(0) if rec["grads"].shape[0] == 1 else None
         # `gradients[name] += param.grad.data` per batch, then abs_ (salun.py:158-165)
         tot = torch.zeros_like(rec["grads"][0])
         for g in rec["grads"]:

@@ -1,0 +1,139 @@
+"""Multi-GPU plumbing of the hot path: one process per GPU, the flat vector sharded across ranks.
+
+Replaces the reference's single-process `torch.nn.DataParallel` (DDPM/runners/diffusion.py:110,...,
+DiT/forget.py:193, DiT/generate_fisher.py:173), whose replicate / scatter / gather / reduce_add runs
+inside torch on GPU 0.  Here:
+
+  * every kernel runs shard-local on the rank's contiguous, 16-element-aligned slice [lo, hi);
+  * the only data-path collectives are
+      - gradients: all-reduce (replicated update) or reduce-scatter (sharded update) of the flat
+        gradient produced by each rank's backward pass               -> `reduce_gradients_`
+      - clip norm: all-reduce of ONE double (the masked sum of squares) -> `reduce_scalar_`
+      - top-k select: all-reduce of the histogram bins (256 KB, then 512 KB) and an all-gather of
+        one tie count per rank                                        -> `reduce_bins_`, `tie_base_`
+      - mask statistics: all-reduce of the zero counts (<= 8 x u64)
+      - weights: all-gather of the updated shard                      -> `all_gather_params_`
+  * collectives are torch.distributed calls (NCCL over NVLink on GPUs; gloo in the CPU tests of the
+    host-side logic) issued on the current stream, so they stay ordered with the kernels.
+
+The pure functions at the top (histogram scan, tie bases) restate on the host what the device
+scan kernel computes; they exist so the cross-rank logic can be tested on CPU with gloo.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import capi
+from .engine import HotPath, OptConfig
+from .flat import shard_bounds
+
+
+# ---- host restatement of the select scan (CPU-testable) -----------------------------------------
+def scan_from_top(bins: torch.Tensor, want: int) -> Tuple[int, int]:
+    """Largest bin B with  above(B) < want <= above(B) + bins[B]; returns (B, above(B)) or (-1, 0)."""
+    if want <= 0:
+        return -1, 0
+    rev = torch.flip(bins.to(torch.int64), dims=[0])
+    incl = torch.cumsum(rev, 0)
+    hit = torch.nonzero(incl >= want)
+    if hit.numel() == 0:
+        return -1, 0
+    j = int(hit[0])
+    b = bins.numel() - 1 - j
+    above = int(incl[j] - rev[j])
+    return b, above
+
+
+def tie_bases(local_eq_counts: Sequence[int]) -> List[int]:
+    """Exclusive prefix over ranks of the per-rank number of threshold-equal keys."""
+    out, run = [], 0
+    for c in local_eq_counts:
+        out.append(run)
+        run += int(c)
+    return out
+
+
+class ShardGroup:
+    """A process group plus the shard arithmetic of one flat vector."""
+
+    def __init__(self, n_total: int, group=None, align: int = 16):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n_total = int(n_total)
+        self.align = align
+        self.bounds = [shard_bounds(self.n_total, self.world, r, align) for r in range(self.world)]
+        self.lo, self.hi = self.bounds[self.rank]
+
+    @property
+    def n_local(self) -> int:
+        return self.hi - self.lo
+
+    def local(self, flat: torch.Tensor) -> torch.Tensor:
+        return flat[self.lo:self.hi]
+
+    def all_reduce_(self, t: torch.Tensor) -> None:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def reduce_gradients_(self, g_full: torch.Tensor, average: bool = True) -> torch.Tensor:
+        """Combine the per-rank gradients of a data-parallel backward pass; returns this rank's shard.
+        (all-reduce: every rank keeps the full summed gradient, as DataParallel's reduce_add leaves on
+        GPU 0; the sharded update only reads its slice.)"""
+        self.all_reduce_(g_full)
+        if average:
+            g_full.div_(self.world)
+        return self.local(g_full)
+
+    def all_gather_params_(self, p_full: torch.Tensor) -> None:
+        """Every rank updated p_full[lo:hi]; make the whole vector consistent again."""
+        shards = [p_full[lo:hi] for lo, hi in self.bounds]
+        if len({s.numel() for s in shards}) == 1 and p_full.is_cuda:
+            dist.all_gather_into_tensor(p_full[:shards[0].numel() * self.world], shards[self.rank], group=self.group)
+        else:
+            # uneven shards (ragged tail): one broadcast per shard, in place
+            for r, s in enumerate(shards):
+                if s.numel():
+                    dist.broadcast(s, src=dist.get_global_rank(self.group, r) if self.group else r, group=self.group)
+
+
+class ShardedHotPath(HotPath):
+    """HotPath over this rank's shard, with the cross-rank reductions filled in."""
+
+    def __init__(self, shards: ShardGroup, device, opt: OptConfig, **kw):
+        super().__init__(shards.n_local, device, opt, **kw)
+        self.shards = shards
+
+    def reduce_scalar_(self, t: torch.Tensor) -> None:
+        self.shards.all_reduce_(t)
+
+    def reduce_bins_(self, bins: torch.Tensor, count: int) -> None:
+        self.shards.all_reduce_(bins[:count])
+
+    def keep_local_bins_(self, bins: torch.Tensor) -> Optional[torch.Tensor]:
+        return bins.clone()
+
+    def tie_base_(self, state: torch.Tensor, local_bins: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        # number of threshold-equal keys on lower ranks: all-gather one count per rank
+        st = capi.read_select_state(state)
+        if st.select_all or st.select_none:
+            return None
+        mine = local_bins[st.thr_key & 0xFFFF].reshape(1).clone()
+        gathered = [torch.zeros_like(mine) for _ in range(self.shards.world)]
+        dist.all_gather(gathered, mine, group=self.shards.group)
+        base = tie_bases([int(x) for x in gathered])[self.shards.rank]
+        return torch.tensor([base], dtype=torch.int64, device=self.device)
+
+    def ratio_mask(self, threshold: float, **kw) -> torch.Tensor:
+        mask = super().ratio_mask(threshold, **kw)
+        self.shards.all_reduce_(self.zero_count)
+        return mask
+
+    def ratio_masks(self, thresholds, **kw) -> torch.Tensor:
+        masks = super().ratio_masks(thresholds, **kw)
+        self.shards.all_reduce_(self.zero_count)
+        return masks

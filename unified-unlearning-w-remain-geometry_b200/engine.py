@@ -63,6 +63,13 @@ class HotPath:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.zero_count = torch.zeros(capi.MAX_THRESHOLDS, dtype=torch.int64, device=self.device)
         self._select = None
+        # optional probe called with a label right after each kernel launch (bench.py records a
+        # CUDA event there to attribute device time per kernel); None on the normal path
+        self.trace = None
+
+    def _t(self, label: str) -> None:
+        if self.trace is not None:
+            self.trace(label)
 
     # ---- lazily allocated role buffers ------------------------------------------------------------
     def buffer(self, role: str, dtype=torch.float32) -> torch.Tensor:
@@ -117,11 +124,13 @@ class HotPath:
         acc = self.buffer({"forget": "forget_fisher", "remain": "remain_fisher"}.get(which, which))
         if clip_max_norm is None:
             capi.fisher_accum(acc, g, divisor)
+            self._t("fisher_accum")
         else:
             self.sumsq.zero_()
             capi.masked_sumsq(g if g.dim() == 1 else g.reshape(-1), None, self.sumsq)
             self.reduce_scalar_(self.sumsq)
             capi.fisher_accum(acc, g, divisor, clip_sumsq=self.sumsq, clip_max_norm=clip_max_norm)
+            self._t("fisher_accum_clipped")
 
     # ---- K2a --------------------------------------------------------------------------------------
     def ratio_mask(self, threshold: float, *, eps: float = 1e-15, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -129,6 +138,7 @@ class HotPath:
         mask = self.mask if out is None else out
         self.zero_count.zero_()
         capi.ratio_mask(self.forget_fisher, self.remain_fisher, threshold, mask, self.zero_count, eps)
+        self._t("ratio_mask")
         return mask
 
     def ratio_masks(self, thresholds: Sequence[float], *, eps: float = 1e-15) -> torch.Tensor:
@@ -217,6 +227,7 @@ class HotPath:
             self.sumsq.zero_()
             capi.masked_sumsq(g, mask if (mask is not None and mask_order == "mask_then_clip") else None, self.sumsq)
             self.reduce_scalar_(self.sumsq)
+            self._t("masked_sumsq")
             clip = self.sumsq
         self.step_count += 1
         a = self._args(flags, ema, max_norm, lr)
@@ -224,6 +235,7 @@ class HotPath:
         capi.fused_update(p, g, None if (sgd and self.opt.momentum == 0.0) else self.m,
                           None if sgd else self.v, mask, self.slow if use_ema else None, a,
                           clip_sumsq=clip, p_bf16=p_bf16)
+        self._t("fused_update_ema" if use_ema else "fused_update")
 
     def forget_step(self, p: torch.Tensor, g: torch.Tensor, *, mask: Optional[torch.Tensor] = None,
                     use_mask: bool = True, max_norm: Optional[float] = None, lr: Optional[float] = None,
