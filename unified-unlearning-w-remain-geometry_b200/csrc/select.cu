@@ -252,8 +252,14 @@ select_scan_kernel(int pass, sfr_select_state* __restrict__ state,
 }
 
 // ---- apply -----------------------------------------------------------------------------------
-// Elements are cut into fixed chunks of kChunk consecutive elements; ordered ties need the
-// number of threshold-equal keys in all earlier chunks (scratch[chunk], exclusive).
+// Elements are cut into fixed chunks of kChunk consecutive elements.  When more keys equal the
+// threshold than the budget allows (the COMMON case at scale: 675 M Gaussian values have ~20
+// elements per distinct fp32 value near the median), the lowest flat indices win, which needs the
+// number of threshold-equal keys in all earlier chunks:
+//   tie_count : scratch[c]            = #ties in chunk c            (streaming read, 4 B/elem)
+//   tie_scan  : scratch[nchunks + c]  = tie_base + #ties before c   (one CTA)
+//   apply     : chunks without ties stream (mask = key > thr); only chunks that contain a
+//               tie pay for the block-wide ordered ranking.
 constexpr int kApplyThreads = 256;
 constexpr int kChunkVecs = 8;                            // float4 per thread per chunk
 constexpr int64_t kChunk = (int64_t)kApplyThreads * 4 * kChunkVecs;  // 8192 elements
@@ -262,8 +268,47 @@ __device__ __forceinline__ bool ties_need_order(const sfr_select_state* s) {
   return !s->select_none && !s->select_all && s->tie_budget != s->count_eq;
 }
 
+// Keys of one chunk, all loads issued before the first use.  A chunk is kChunkVecs slabs of
+// kApplyThreads float4; thread t owns elements [base + (slab*256 + t)*4, +4), so flat order ==
+// (slab, thread, component) order.  Out-of-range elements get key 0 and valid bit 0.
 template <int MODE>
-__global__ void __launch_bounds__(kApplyThreads, 4)
+__device__ __forceinline__ void load_chunk_keys(const float* __restrict__ a, const float* __restrict__ b,
+                                                float eps, int64_t n, int64_t base,
+                                                uint32_t (&key)[kChunkVecs][4], uint32_t& valid_bits) {
+  valid_bits = 0;
+  if (base + kChunk <= n) {
+    float4 x[kChunkVecs], y[kChunkVecs];
+#pragma unroll
+    for (int sl = 0; sl < kChunkVecs; ++sl) {
+      const int64_t e0 = base + ((int64_t)sl * kApplyThreads + threadIdx.x) * 4;
+      x[sl] = ld_stream(reinterpret_cast<const float4*>(a + e0));
+      if constexpr (MODE == SFR_KEY_RATIO) y[sl] = ld_stream(reinterpret_cast<const float4*>(b + e0));
+      else y[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int sl = 0; sl < kChunkVecs; ++sl) {
+      key[sl][0] = key_from<MODE>(x[sl].x, y[sl].x, eps);
+      key[sl][1] = key_from<MODE>(x[sl].y, y[sl].y, eps);
+      key[sl][2] = key_from<MODE>(x[sl].z, y[sl].z, eps);
+      key[sl][3] = key_from<MODE>(x[sl].w, y[sl].w, eps);
+    }
+    valid_bits = 0xffffffffu;
+  } else {  // the last, ragged chunk
+#pragma unroll
+    for (int sl = 0; sl < kChunkVecs; ++sl) {
+      const int64_t e0 = base + ((int64_t)sl * kApplyThreads + threadIdx.x) * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool ok = e0 + q < n;
+        key[sl][q] = ok ? key_from<MODE>(a[e0 + q], MODE == SFR_KEY_RATIO ? b[e0 + q] : 0.f, eps) : 0u;
+        valid_bits |= (ok ? 1u : 0u) << (sl * 4 + q);
+      }
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kApplyThreads, MODE == SFR_KEY_RATIO ? 2 : 4)
 select_tie_count_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps,
                         int64_t n, const sfr_select_state* __restrict__ state,
                         unsigned long long* __restrict__ scratch) {
@@ -272,12 +317,13 @@ select_tie_count_kernel(const float* __restrict__ a, const float* __restrict__ b
   const uint32_t thr = state->thr_key;
   const int64_t nchunks = (n + kChunk - 1) / kChunk;
   for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-    const int64_t base = c * kChunk;
+    uint32_t key[kChunkVecs][4], valid;
+    load_chunk_keys<MODE>(a, b, eps, n, c * kChunk, key, valid);
     unsigned int cnt = 0;
-    for (int j = 0; j < kChunkVecs * 4; ++j) {
-      const int64_t i = base + (int64_t)j * kApplyThreads + threadIdx.x;
-      if (i < n) cnt += key_from<MODE>(a[i], MODE == SFR_KEY_RATIO ? b[i] : 0.f, eps) == thr;
-    }
+#pragma unroll
+    for (int sl = 0; sl < kChunkVecs; ++sl)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cnt += ((valid >> (sl * 4 + q)) & 1u) && key[sl][q] == thr;
     cnt = block_sum<unsigned int>(cnt, red);
     if (threadIdx.x == 0) scratch[c] = cnt;
     __syncthreads();
@@ -304,23 +350,71 @@ select_tie_scan_kernel(int64_t nchunks, const sfr_select_state* __restrict__ sta
       part[threadIdx.x] += add;
       __syncthreads();
     }
-    if (i < nchunks) scratch[i] = carry + part[threadIdx.x] - mine;  // exclusive
+    if (i < nchunks) scratch[nchunks + i] = carry + part[threadIdx.x] - mine;  // exclusive
     __syncthreads();
     if (threadIdx.x == 0) carry += part[1023];
     __syncthreads();
   }
 }
 
+// No tie needs ordering (tie_budget == count_eq, or select all / none):
+//   mask = key >= thr       — a pure stream: 4 (8) B read + 1 B written per element.
+constexpr int kApplyUnroll = 4;
+
 template <int MODE>
 __global__ void __launch_bounds__(kApplyThreads, 4)
+select_apply_stream_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps,
+                           int64_t n, const sfr_select_state* __restrict__ state,
+                           uint8_t* __restrict__ mask) {
+  if (ties_need_order(state)) return;  // the ordered kernel below writes the mask instead
+  const bool none = state->select_none != 0;
+  const bool all = state->select_all != 0;
+  const uint32_t thr = all ? 0u : state->thr_key;  // all: every key (NaN's 0 included) >= 0
+  const int64_t nvec = n >> 2;
+  const int64_t tile = (int64_t)kApplyThreads * kApplyUnroll;
+  const int64_t ntiles = (nvec + tile - 1) / tile;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  unsigned int* m4 = reinterpret_cast<unsigned int*>(mask);
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * tile + threadIdx.x;
+    float4 x[kApplyUnroll], y[kApplyUnroll];
+#pragma unroll
+    for (int u = 0; u < kApplyUnroll; ++u) {
+      const int64_t v = base + (int64_t)u * kApplyThreads;
+      const bool in = v < nvec;
+      x[u] = in ? ld_stream(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (MODE == SFR_KEY_RATIO)
+        y[u] = in ? ld_stream(b4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      else
+        y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kApplyUnroll; ++u) {
+      const int64_t v = base + (int64_t)u * kApplyThreads;
+      if (v >= nvec) continue;
+      const uint32_t s0 = !none && key_from<MODE>(x[u].x, y[u].x, eps) >= thr;
+      const uint32_t s1 = !none && key_from<MODE>(x[u].y, y[u].y, eps) >= thr;
+      const uint32_t s2 = !none && key_from<MODE>(x[u].z, y[u].z, eps) >= thr;
+      const uint32_t s3 = !none && key_from<MODE>(x[u].w, y[u].w, eps) >= thr;
+      __stcs(m4 + v, s0 | (s1 << 8) | (s2 << 16) | (s3 << 24));
+    }
+  }
+  const int64_t tail0 = nvec << 2;
+  if (blockIdx.x == 0 && threadIdx.x < (n - tail0)) {
+    const int64_t i = tail0 + threadIdx.x;
+    mask[i] = (uint8_t)(!none && key_from<MODE>(a[i], MODE == SFR_KEY_RATIO ? b[i] : 0.f, eps) >= thr);
+  }
+}
+
+// More threshold-equal keys than the budget: lowest flat index first.
+template <int MODE>
+__global__ void __launch_bounds__(kApplyThreads, MODE == SFR_KEY_RATIO ? 2 : 4)
 select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps,
                     int64_t n, const sfr_select_state* __restrict__ state,
                     const unsigned long long* __restrict__ scratch, uint8_t* __restrict__ mask) {
+  if (!ties_need_order(state)) return;  // the streaming kernel above wrote the mask
   __shared__ unsigned int warp_tot[kApplyThreads / 32];
-  __shared__ unsigned long long chunk_run;
-  const bool none = state->select_none != 0;
-  const bool all = state->select_all != 0;
-  const bool ordered = ties_need_order(state);
   const uint32_t thr = state->thr_key;
   const unsigned long long budget = state->tie_budget;
   const int64_t nchunks = (n + kChunk - 1) / kChunk;
@@ -328,41 +422,22 @@ select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
 
   for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const int64_t base = c * kChunk;
-    if (ordered) {
-      if (threadIdx.x == 0) chunk_run = scratch[c];
-      __syncthreads();
-    }
-    // a chunk is kChunkVecs slabs of kApplyThreads float4; thread t owns elements
-    // [slab*1024 + 4t, +4) so that flat order == (slab, thread, component) order
+    const unsigned long long chunk_ties = scratch[c];        // uniform over the CTA
+    unsigned long long run = scratch[nchunks + c];           // ties before this chunk
+    uint32_t key[kChunkVecs][4], valid;
+    load_chunk_keys<MODE>(a, b, eps, n, base, key, valid);
+#pragma unroll
     for (int sl = 0; sl < kChunkVecs; ++sl) {
       const int64_t e0 = base + ((int64_t)sl * kApplyThreads + threadIdx.x) * 4;
-      uint32_t key[4];
-      bool valid[4];
-      if (e0 + 3 < n) {
-        const float4 x = ld_stream(reinterpret_cast<const float4*>(a + e0));
-        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-        if constexpr (MODE == SFR_KEY_RATIO) y = ld_stream(reinterpret_cast<const float4*>(b + e0));
-        key[0] = key_from<MODE>(x.x, y.x, eps);
-        key[1] = key_from<MODE>(x.y, y.y, eps);
-        key[2] = key_from<MODE>(x.z, y.z, eps);
-        key[3] = key_from<MODE>(x.w, y.w, eps);
-        valid[0] = valid[1] = valid[2] = valid[3] = true;
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          valid[q] = e0 + q < n;
-          key[q] = valid[q] ? key_from<MODE>(a[e0 + q], MODE == SFR_KEY_RATIO ? b[e0 + q] : 0.f, eps) : 0u;
-        }
-      }
       uint32_t sel[4];
-      if (!ordered) {
+      if (chunk_ties == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) sel[q] = all ? 1u : (none ? 0u : (key[q] >= thr));
+        for (int q = 0; q < 4; ++q) sel[q] = key[sl][q] > thr;
       } else {
         unsigned int tq[4], mine = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          tq[q] = valid[q] && key[q] == thr;
+          tq[q] = ((valid >> (sl * 4 + q)) & 1u) && key[sl][q] == thr;
           mine += tq[q];
         }
         // exclusive prefix of tie counts in flat order: warp scan, then across warps
@@ -372,6 +447,7 @@ select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
           const unsigned int up = __shfl_up_sync(kFullMask, incl, o);
           if (lane >= o) incl += up;
         }
+        __syncthreads();  // warp_tot of the previous slab fully consumed
         if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
         unsigned int before = 0, slab_total = 0;
@@ -381,23 +457,21 @@ select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
           if (w < warp) before += t;
           slab_total += t;
         }
-        unsigned long long rank = chunk_run + before + (incl - mine);
+        unsigned long long rank = run + before + (incl - mine);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          sel[q] = key[q] > thr || (tq[q] && rank < budget);
+          sel[q] = key[sl][q] > thr || (tq[q] && rank < budget);
           rank += tq[q];
         }
-        __syncthreads();
-        if (threadIdx.x == 0) chunk_run += slab_total;
-        __syncthreads();
+        run += slab_total;  // every thread keeps the same running count
       }
-      if (e0 + 3 < n) {
+      if (((valid >> (sl * 4)) & 0xfu) == 0xfu) {
         __stcs(reinterpret_cast<unsigned int*>(mask + e0),
                sel[0] | (sel[1] << 8) | (sel[2] << 16) | (sel[3] << 24));
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (valid[q]) mask[e0 + q] = (uint8_t)sel[q];
+          if ((valid >> (sl * 4 + q)) & 1u) mask[e0 + q] = (uint8_t)sel[q];
       }
     }
   }
@@ -476,8 +550,8 @@ extern "C" int sfr_select_scan(int pass, sfr_select_state* state, unsigned long 
 }
 
 extern "C" int64_t sfr_select_scratch_elems(int64_t n) {
-  if (n <= 0) return 1;
-  return (n + sfr::kChunk - 1) / sfr::kChunk;
+  if (n <= 0) return 2;
+  return 2 * ((n + sfr::kChunk - 1) / sfr::kChunk);  // per-chunk tie counts + their exclusive scan
 }
 
 extern "C" int sfr_select_apply(const float* a, const float* b, int key_mode, float eps,
@@ -501,14 +575,18 @@ extern "C" int sfr_select_apply(const float* a, const float* b, int key_mode, fl
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t nchunks = (n + kChunk - 1) / kChunk;
   const int grid = persistent_grid(nchunks, 8);
+  const int64_t stile = (int64_t)kApplyThreads * kApplyUnroll;
+  const int sgrid = persistent_grid(((n >> 2) + stile - 1) / stile, 4);
   if (key_mode == SFR_KEY_ABS) {
     select_tie_count_kernel<SFR_KEY_ABS><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch);
     select_tie_scan_kernel<<<1, 1024, 0, s>>>(nchunks, state, tie_base, scratch);
     select_apply_kernel<SFR_KEY_ABS><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch, mask);
+    select_apply_stream_kernel<SFR_KEY_ABS><<<sgrid, kApplyThreads, 0, s>>>(a, b, eps, n, state, mask);
   } else {
     select_tie_count_kernel<SFR_KEY_RATIO><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch);
     select_tie_scan_kernel<<<1, 1024, 0, s>>>(nchunks, state, tie_base, scratch);
     select_apply_kernel<SFR_KEY_RATIO><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch, mask);
+    select_apply_stream_kernel<SFR_KEY_RATIO><<<sgrid, kApplyThreads, 0, s>>>(a, b, eps, n, state, mask);
   }
   SFR_LAUNCH_STATUS();
 }
