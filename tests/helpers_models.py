@@ -1,0 +1,46 @@
+"""Tiny models / loaders shared by the tests; the same definitions tests/golden/make_golden.py used
+when it recorded the reference runs (kept in sync by hand: 554-parameter TinyNet, TinyDiT)."""
+import torch
+import torch.nn as nn
+from torch.utils.data import DataLoader, TensorDataset
+
+
+class TinyNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv = nn.Conv2d(3, 8, 3, padding=1)
+        self.fc = nn.Linear(32, 10)
+
+    def forward(self, x):
+        x = torch.relu(self.conv(x))
+        x = torch.nn.functional.adaptive_avg_pool2d(x, 2).flatten(1)
+        return self.fc(x)
+
+
+class TinyDiT(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.pos_embed = nn.Parameter(torch.randn(1, 6, 8), requires_grad=False)
+        self.fc = nn.Linear(33, 10)
+        self.out = nn.Linear(10, 4)
+
+
+def loaders(seed):
+    g = torch.Generator().manual_seed(seed)
+    fx, fy = torch.randn(12, 3, 8, 8, generator=g), torch.randint(0, 10, (12,), generator=g)
+    rx, ry = torch.randn(16, 3, 8, 8, generator=g), torch.randint(0, 10, (16,), generator=g)
+    mk = lambda x, y: DataLoader(TensorDataset(x, y), batch_size=4, shuffle=False)
+    return dict(forget_train=mk(fx, fy), retain_train=mk(rx, ry), forget_valid=None, retain_valid=None)
+
+
+def inject(model, flat_grad):
+    """A 'loss' whose gradient w.r.t. the trainable parameters is exactly `flat_grad`:
+    sum_i <p_i, g_i>.  Lets a test drive a real backward pass with recorded gradients."""
+    loss, off = 0.0, 0
+    for p in model.parameters():
+        if p.requires_grad:
+            g = flat_grad[off:off + p.numel()].reshape(p.shape).to(p.device)
+            loss = loss + (p * g).sum()
+            off += p.numel()
+    assert off == flat_grad.numel()
+    return loss

@@ -1,0 +1,106 @@
+"""world_size-2 tests of the multi-GPU host logic on CPU (gloo): shard arithmetic, the collectives
+the path uses, and the cross-rank protocol of the top-k select (histogram all-reduce -> scan ->
+filtered histogram all-reduce -> scan -> per-rank tie bases), with the oracle's key function
+standing in for the CUDA histogram kernels (which need a GPU)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+WORLD = 2
+
+
+def _worker(rank, port, fn_name, tmp):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(WORLD))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        globals()[fn_name](rank, tmp)
+    finally:
+        dist.destroy_process_group()
+
+
+def _spawn(fn_name, tmp_path):
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(port, fn_name, str(tmp_path)), nprocs=WORLD, join=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def _shards_and_collectives(rank, tmp):
+    from sfron_b200.dist import ShardGroup
+    n = 1000 + 37                                        # ragged: not a multiple of 16 * world
+    sg = ShardGroup(n)
+    assert sg.bounds[0][0] == 0 and sg.bounds[-1][1] == n and sg.bounds[0][1] == sg.bounds[1][0]
+    assert sg.lo % 16 == 0
+    # gradient all-reduce (mean over ranks) and the shard view
+    g = torch.full((n,), float(rank + 1))
+    shard = sg.reduce_gradients_(g, average=True)
+    assert torch.allclose(g, torch.full((n,), 1.5)) and shard.numel() == sg.n_local
+    assert shard.data_ptr() == g[sg.lo:].data_ptr()      # a view, not a copy
+    # clip-norm scalar: sum of the per-shard sums of squares == the global one
+    full = torch.arange(n, dtype=torch.float64)
+    part = sg.local(full).pow(2).sum().reshape(1)
+    sg.all_reduce_(part)
+    assert part.item() == full.pow(2).sum().item()
+    # all-gather of the updated weights, uneven shards
+    p = torch.zeros(n)
+    sg.local(p).fill_(rank + 1.0)
+    sg.all_gather_params_(p)
+    want = torch.cat([torch.full((hi - lo,), r + 1.0) for r, (lo, hi) in enumerate(sg.bounds)])
+    assert torch.equal(p, want)
+
+
+def _select_protocol(rank, tmp):
+    from oracle import sfron_oracle as O
+    from sfron_b200.dist import ShardGroup, scan_from_top, tie_bases
+    g = torch.Generator().manual_seed(0)
+    n = 40_003
+    x = torch.randint(0, 40, (n,), generator=g).float() * 0.125        # heavy ties
+    x[torch.rand(n, generator=g) < 0.2] = 0.0
+    x *= torch.where(torch.rand(n, generator=g) < 0.5, -1.0, 1.0)
+    sg = ShardGroup(n)
+    mine = sg.local(x)
+    key = O.select_key(mine)
+    for k in (1, n // 7, n // 2, n - 5, n):
+        # pass 0: histogram of key[30:16], all-reduced
+        bins0 = torch.bincount(key >> 16, minlength=32768)
+        sg.all_reduce_(bins0)
+        prefix, above0 = scan_from_top(bins0, k)
+        assert prefix >= 0
+        k_in_bin = k - above0
+        # pass 1: low 16 bits of the keys matching the prefix
+        sel = (key >> 16) == prefix
+        local_bins1 = torch.bincount(key[sel] & 0xFFFF, minlength=65536)
+        bins1 = local_bins1.clone()
+        sg.all_reduce_(bins1)
+        b, above1 = scan_from_top(bins1, k_in_bin)
+        thr = (prefix << 16) | b
+        budget = k_in_bin - above1
+        # tie bases: all-gather one count per rank
+        eq_local = local_bins1[b].reshape(1)
+        gathered = [torch.zeros_like(eq_local) for _ in range(WORLD)]
+        dist.all_gather(gathered, eq_local)
+        base = tie_bases([int(t) for t in gathered])[rank]
+        # apply, shard-local
+        tie = key == thr
+        rank_in_ties = base + torch.cumsum(tie.to(torch.int64), 0) - 1
+        local_mask = (key > thr) | (tie & (rank_in_ties < budget))
+        want = sg.local(O.topk_mask_flat(x, k)).bool()
+        assert torch.equal(local_mask, want), (rank, k)
+
+
+def test_shards_and_collectives(tmp_path):
+    _spawn("_shards_and_collectives", tmp_path)
+
+
+def test_select_protocol_two_ranks(tmp_path):
+    _spawn("_select_protocol", tmp_path)

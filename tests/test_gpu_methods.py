@@ -1,0 +1,198 @@
+"""GPU tests of the drop-in entry points (sfron_b200.methods) against the reference-generated
+golden fixtures: same class / CLI surface, same files, same results."""
+import argparse
+import os
+
+import pytest
+import torch
+import torch.nn as nn
+
+from conftest import load_golden, unflat
+from helpers_models import TinyDiT, TinyNet, inject, loaders
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def close(a, b, rtol=1e-6):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    rms = b.pow(2).mean().sqrt().item()
+    return bool(((a - b).abs() <= rtol * (b.abs() + rms)).all())
+
+
+def set_flat(model, flat, names, shapes):
+    vals = unflat(flat, names, shapes)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            p.copy_(vals[n])
+
+
+@pytest.mark.parametrize("tag", ["default", "beta09"])
+def test_classification_sfron_dropin(dev, tmp_path, tag):
+    """The whole method (Fisher -> mask -> loop) with the real model forward/backward on the GPU,
+    against the reference's CPU run: GPU conv/matmul rounding differs from CPU's, so the comparison is
+    looser than the kernel-level parity tests (which replay identical gradients)."""
+    from sfron_b200.methods import create_unlearn_method
+    fx = load_golden(f"cls_sfron_{tag}.pt")
+    h = fx["hyper"]
+    torch.manual_seed(0)
+    model = TinyNet()
+    set_flat(model, fx["theta0"], fx["names"], fx["shapes"])
+    model = model.to(dev)
+    args = argparse.Namespace(num_classes=10, seed=0)
+    method = create_unlearn_method("SFRon")(model, nn.CrossEntropyLoss(), str(tmp_path), args)
+    method.n_iters, method.forget_freq, method.log_freq = h["n_iters"], h["forget_freq"], 10 ** 9
+    method.ema_beta = h["ema_beta"]
+    method.prepare_unlearn(loaders(1))
+    # files in the reference's format
+    for which in ("forget", "remain"):
+        d = torch.load(tmp_path / f"{which}_fisher.pt", weights_only=False)
+        assert list(d.keys()) == fx["names"]
+        got = torch.cat([d[n].reshape(-1) for n in fx["names"]])
+        assert got.dtype == torch.float32 and got.device.type == "cpu"
+        assert torch.allclose(got, fx[f"{which}_fisher"], rtol=1e-3, atol=1e-9)
+    mask = method.weight_saliency_mask
+    got_mask = torch.cat([mask[n].reshape(-1) for n in fx["names"]])
+    assert got_mask.dtype == torch.bool
+    assert (got_mask.to(torch.uint8) == fx["mask"]).float().mean() > 0.99
+    out = method.get_unlearned_model()
+    assert out is model
+    final = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu()
+    assert torch.allclose(final, fx["theta_final"], rtol=0, atol=5e-3)
+    assert (final - fx["theta0"]).abs().max() > 1e-3          # it did move
+    assert set(method.get_params()) >= {"opt", "momentum", "weight_decay", "retain_lr", "n_iters", "threshold"}
+    # second construction reuses the cached Fisher files (sfron.py:269-271,296-298)
+    m2 = create_unlearn_method("SFRon")(model, nn.CrossEntropyLoss(), str(tmp_path), args)
+    m2.prepare_unlearn(loaders(1))
+    got2 = torch.cat([m2.weight_saliency_mask[n].reshape(-1) for n in fx["names"]])
+    assert torch.equal(got2, got_mask)
+    with pytest.raises(NotImplementedError):
+        create_unlearn_method("SCRUB")
+
+
+def test_salun_topk_dropin(dev, tmp_path):
+    from sfron_b200.methods import create_unlearn_method
+    fx = load_golden("salun_topk.pt")
+    for th in ("0.2", "0.5"):
+        torch.manual_seed(3)
+        model = TinyNet().to(dev)
+        args = argparse.Namespace(num_classes=10, seed=0, batch_size=4)
+        method = create_unlearn_method("SalUn")(model, nn.CrossEntropyLoss(), str(tmp_path), args)
+        method.th = float(th)
+        hard = method.get_gradient_ratio(loaders(2)["forget_train"])
+        got = torch.cat([hard[n].reshape(-1) for n in fx["names"]])
+        assert got.dtype == torch.int64 and int(got.sum()) == int(got.numel() * float(th))
+        assert (got == fx[th]["mask"]).float().mean() > 0.99     # GPU vs CPU backward rounding
+
+
+def test_mask_clis_match_reference_scripts(dev, tmp_path):
+    from sfron_b200.methods import masks
+    # DDPM / SD: --ckpt_folder / --threshold, outputs fisher_{th}.pt / nude_mask_{th}.pt
+    for fam, fixture, fn, rn, out in (("ddpm", "ddpm_ratio_mask.pt", "forget_fisher.pt", "remain_fisher.pt", "fisher_{}.pt"),
+                                      ("sd", "sd_ratio_mask.pt", "nude_forget.pt", "nude_remain.pt", "nude_mask_{}.pt")):
+        fx = load_golden(fixture)
+        folder = tmp_path / fam
+        folder.mkdir()
+        torch.save(fx["forget"], folder / fn)
+        torch.save(fx["remain"], folder / rn)
+        for th_s, ref in fx["masks"].items():
+            masks.main([fam, "--ckpt_folder", str(folder), "--threshold", th_s])
+            got = torch.load(folder / out.format(float(th_s)), weights_only=False)
+            assert list(got.keys()) == list(ref.keys())
+            assert all(got[n].dtype == torch.bool and torch.equal(got[n], ref[n]) for n in ref)
+    # DiT: --mask-path / --forget-class / --thresholds, int-0 placeholder preserved
+    fx = load_golden("dit_ratio_mask.pt")
+    folder = tmp_path / "dit" / "7"
+    folder.mkdir(parents=True)
+    torch.save(fx["forget"], folder / "forget_fisher.pt")
+    torch.save(fx["remain"], folder / "remain_fisher.pt")
+    masks.generate_mask_dit(str(tmp_path / "dit"), [7], [0.5, 1, 3, 5, 10])
+    for th_s, ref in fx["masks"].items():
+        got = torch.load(folder / f"fisher_{th_s}.pt", weights_only=False)
+        assert list(got.keys()) == list(ref.keys())
+        for n, r in ref.items():
+            if torch.is_tensor(r):
+                assert torch.equal(got[n], r)
+            else:
+                assert got[n] == 0 and not torch.is_tensor(got[n])
+
+
+def test_dit_family_loop_and_checkpoint(dev):
+    from sfron_b200.methods.diffusion import DiffusionUnlearner
+    fx = load_golden("dit_adamw_ema_loop.pt")
+    names, shapes = [n[len("module."):] for n in fx["names"]], {k[len("module."):]: v for k, v in fx["shapes"].items()}
+    model = TinyDiT()
+    set_flat(model, fx["theta0"], names, shapes)
+    model = model.to(dev)
+    un = DiffusionUnlearner(model, "dit", lr=fx["hyper"]["lr"])
+    tnames = fx["train_names"]
+    tshapes = {n: fx["shapes"][n] for n in tnames}
+    un.load_mask(unflat(fx["mask"], tnames, tshapes))          # keys carry "module.", like the reference file
+    gf, gr = fx["forget_grads"], fx["remain_grads"]
+    un.forget(len(gf), lambda i: inject(model, gf[i]), lambda i: inject(model, gr[i]))
+    final = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    assert close(final, fx["theta_final"])
+    ckpt = un.checkpoint(step=len(gf), args=argparse.Namespace(lr=1e-4))
+    assert set(ckpt) == {"model", "ema", "opt", "args"}
+    assert list(ckpt["model"].keys()) == fx["names"]                # DataParallel-prefixed, as model.state_dict()
+    ema = torch.cat([ckpt["ema"][n].reshape(-1) for n in names])     # ema = deepcopy(model): bare names
+    assert close(ema, fx["ema_final"])
+    # the optimizer slot loads into the reference's optimizer
+    ref_model = nn.DataParallel(TinyDiT())
+    opt = torch.optim.AdamW(ref_model.parameters(), lr=1e-4, weight_decay=0)
+    opt.load_state_dict(ckpt["opt"])
+    assert float(opt.state[ref_model.module.fc.weight]["step"]) == 2 * len(gf)
+
+
+def test_ddpm_family_loop_fisher_and_topk(dev, tmp_path):
+    from sfron_b200.methods.diffusion import DiffusionUnlearner
+    fx = load_golden("ddpm_adam_ema_loop.pt")
+    h = fx["hyper"]
+    names = [n[len("module."):] for n in fx["names"]]
+    shapes = {k[len("module."):]: v for k, v in fx["shapes"].items()}
+    model = TinyNet()
+    set_flat(model, fx["theta0"], names, shapes)
+    model = model.to(dev)
+    un = DiffusionUnlearner(model, "ddpm", lr=h["lr"])
+    un.load_mask({n: m for n, m in unflat(fx["mask"], fx["names"], fx["shapes"]).items()})
+    gf, gr = fx["forget_grads"], fx["remain_grads"]
+    un.forget(len(gf), lambda i: inject(model, gf[i]), lambda i: inject(model, gr[i]))
+    final = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    assert close(final, fx["theta_final"])
+    states = un.checkpoint(step=5)
+    assert isinstance(states, list) and len(states) == 4 and states[2] == 5
+    assert close(torch.cat([states[3][n].reshape(-1) for n in names]), fx["ema_final"])
+    assert close(torch.cat([states[1]["state"][i]["exp_avg_sq"].reshape(-1) for i in range(4)]), fx["exp_avg_sq"])
+    # DDPM Fisher: clipped gradient, files with module.-prefixed keys
+    from oracle import sfron_oracle as O
+    acc = O.fisher_init(fx["names"])
+    for g in gf:
+        O.fisher_accumulate_clipped(acc, unflat(g, fx["names"], fx["shapes"]), len(gf), h["grad_clip"])
+    un.generate_fisher("forget", len(gf), lambda i: inject(model, gf[i]), out_dir=str(tmp_path))
+    d = torch.load(tmp_path / "forget_fisher.pt", weights_only=False)
+    assert list(d.keys()) == fx["names"]
+    assert close(torch.cat([d[n].reshape(-1) for n in fx["names"]]), torch.cat([acc[n].reshape(-1) for n in fx["names"]]))
+    # SalUn top-k mask of the DDPM runner on the golden gradients (no clip: family preset overridden)
+    sx = load_golden("salun_topk.pt")
+    un2 = DiffusionUnlearner(TinyNet().to(dev), "ddpm", clip_fisher=None)
+    grads = sx["0.5"]["grads"]
+    hard = un2.generate_topk_mask(len(grads), lambda i: inject(un2.model, grads[i]), ratio=0.5,
+                                  path=str(tmp_path / "mask" / "with_0.5.pt"))
+    saved = torch.load(tmp_path / "mask" / "with_0.5.pt", weights_only=False)
+    got = torch.cat([saved["module." + n].reshape(-1) for n in sx["names"]])
+    assert got.dtype == torch.int64 and torch.equal(got, sx["0.5"]["mask"])
+    # per-sample FIM rows
+    rows = torch.randn(3, un2.mhp.layout.numel + 2, device=dev)[:, :un2.mhp.layout.numel]
+    fim = un2.save_fim([rows[:2], rows[2:]], dataset_len=10, path=str(tmp_path / "fisher_dict.pkl"))
+    want = torch.zeros(un2.mhp.layout.numel)
+    for r in rows.cpu():
+        want += r ** 2 / 10
+    assert torch.equal(fim.cpu(), want)
+    import pickle
+    with open(tmp_path / "fisher_dict.pkl", "rb") as f:
+        assert list(pickle.load(f).keys()) == ["module." + n for n in sx["names"]]

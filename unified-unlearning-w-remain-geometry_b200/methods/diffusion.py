@@ -1,0 +1,162 @@
+"""Hot-path halves of the diffusion entry points, over caller-supplied loss closures.
+
+The reference's diffusion scripts interleave the path with dataset / VAE / sampler code that is
+out of scope.  `DiffusionUnlearner` keeps the path itself — the order of
+operations, hyper-parameter defaults, file names and dict formats of each family — and takes the
+model plus closures that produce the (already alpha-weighted) losses:
+
+  family "ddpm"  Diffusion.generate_fisher / generate_mask / save_fim / sfron_forget / saliency_unlearn
+                 DDPM/runners/diffusion.py:1210-1364, 930-1036, 262-352, 1038-1208, 479-616
+  family "dit"   DiT/generate_fisher.py:216-291, DiT/forget.py:256-355
+  family "sd"    SD/train-scripts/generate_fisher.py:31-129, nsfw_removal.py:108-173
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from dataclasses import dataclass
+from typing import Callable, Dict, Iterable, Optional
+
+import torch
+
+from .. import capi, formats
+from ..engine import OptConfig
+from .common import ModelHotPath, cosine_lr_scheduler
+
+
+@dataclass
+class FamilyPreset:
+    opt: OptConfig
+    ema_mode: str
+    ema_a: float
+    key_prefix: str            # prefix of the reference's file keys (DataParallel's "module.")
+    clip_forget: Optional[float]
+    clip_remain: Optional[float]
+    clip_fisher: Optional[float]
+    forget_fisher_name: str = "forget_fisher.pt"
+    remain_fisher_name: str = "remain_fisher.pt"
+
+
+def preset(family: str, **over) -> FamilyPreset:
+    if family == "ddpm":      # configs/cifar10_sfron.yml: Adam lr 1e-4 beta1 .9 eps 1e-8 wd 0, grad_clip 1.0, ema_rate 1e-4
+        p = FamilyPreset(OptConfig("adam", lr=over.pop("lr", 1e-4), beta1=0.9, beta2=0.999, eps=1e-8,
+                                   weight_decay=0.0), "ddpm", 1e-4, "module.", 1.0, 1.0, 1.0)
+    elif family == "dit":     # DiT/forget.py:199 AdamW(lr, wd=0); --grad-clip 1.0 on the forget step only; EMA 0.9999
+        p = FamilyPreset(OptConfig("adamw", lr=over.pop("lr", 1e-4), weight_decay=0.0), "dit", 0.9999,
+                         "module.", 1.0, None, None)
+    elif family == "sd":      # nsfw_removal.py:81 Adam(lr); no clip, no EMA; U-Net-local key names
+        p = FamilyPreset(OptConfig("adam", lr=over.pop("lr", 1e-5)), "none", 0.0, "", None, None, None,
+                         forget_fisher_name="nude_forget.pt", remain_fisher_name="nude_remain.pt")
+    else:
+        raise ValueError(family)
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+LossFn = Callable[[int], torch.Tensor]
+
+
+class DiffusionUnlearner:
+    def __init__(self, model: torch.nn.Module, family: str = "dit", *, device=None, **preset_overrides):
+        self.family = family
+        self.cfg = preset(family, **preset_overrides)
+        self.model = model
+        self.mhp = ModelHotPath(model, self.cfg.opt, ema_mode=self.cfg.ema_mode, ema_a=self.cfg.ema_a,
+                                key_prefix=self.cfg.key_prefix, device=device)
+
+    # ---- Fisher ------------------------------------------------------------------------------------
+    def generate_fisher(self, which: str, n_batches: int, loss_fn: LossFn, out_dir: Optional[str] = None) -> None:
+        """`F += grad**2 / n_batches` over `n_batches` backward passes of `loss_fn(i)`; written in the
+        reference's dict format to {out_dir}/{forget,remain}_fisher.pt (nude_*.pt for SD)."""
+        mhp = self.mhp
+        mhp.hp.buffer(f"{which}_fisher").zero_()
+        for i in range(n_batches):
+            mhp.zero_grad()
+            loss_fn(i).backward()
+            mhp.fisher_accumulate(which, float(n_batches), clip_max_norm=self.cfg.clip_fisher)
+        mhp.zero_grad()
+        if out_dir is not None:
+            os.makedirs(out_dir, exist_ok=True)
+            name = self.cfg.forget_fisher_name if which == "forget" else self.cfg.remain_fisher_name
+            mhp.save_fisher(which, os.path.join(out_dir, name))
+
+    def save_fim(self, per_sample_grads: Iterable[torch.Tensor], dataset_len: int, path: Optional[str] = None):
+        """Per-sample FIM of DDPM save_fim: every item is a [B, n] (or [n]) block of per-sample
+        gradients summed over the timesteps; F += row**2 / |D| row by row (runners/diffusion.py:337-344)."""
+        acc = self.mhp.hp.buffer("fim")
+        acc.zero_()
+        for rows in per_sample_grads:
+            capi.fisher_accum(acc, rows, float(dataset_len))
+        if path is not None:
+            formats.save_fim_pickle(path, self.mhp.layout, acc, prefix=self.cfg.key_prefix)
+        return acc
+
+    # ---- masks -------------------------------------------------------------------------------------
+    def ratio_mask(self, threshold: float, out_dir: Optional[str] = None, name_fmt: str = "fisher_{th}.pt"):
+        mask = self.mhp.ratio_mask(threshold)
+        if out_dir is not None:
+            torch.save(mask, os.path.join(out_dir, name_fmt.format(th=formats.threshold_tag(threshold))))
+        return mask
+
+    def generate_topk_mask(self, n_batches: int, loss_fn: LossFn, ratio: float = 0.5,
+                           path: Optional[str] = None) -> Dict[str, object]:
+        """SalUn mask of DDPM generate_mask: sum of the (clipped) batch gradients, |.|, global
+        top-`ratio` -> int64 0/1 (runners/diffusion.py:955-1036)."""
+        mhp = self.mhp
+        acc = mhp.hp.buffer("grad_sum")
+        acc.zero_()
+        for i in range(n_batches):
+            mhp.zero_grad()
+            loss_fn(i).backward()
+            g = mhp.grads()
+            if self.cfg.clip_fisher is not None:      # clip_grad_norm_ before accumulating (:985-990)
+                mhp.hp.sumsq.zero_()
+                capi.masked_sumsq(g, None, mhp.hp.sumsq)
+                coef = torch.clamp(self.cfg.clip_fisher / (mhp.hp.sumsq.sqrt().float() + 1e-6), max=1.0)
+                acc += g.mul(coef)                   # grad.mul_(coef) ; gradients[name] += grad
+            else:
+                acc += g
+        mhp.zero_grad()
+        k = int(mhp.layout.numel * ratio)
+        mask = mhp.hp.topk_mask(acc, k)
+        out = formats.topk_mask_to_dict(mhp.layout, mask, all_names=mhp.flat.all_names, prefix=self.cfg.key_prefix)
+        if path is not None:
+            os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+            torch.save(out, path)
+        return out
+
+    def load_mask(self, path_or_dict) -> None:
+        self.mhp.load_mask(path_or_dict)
+
+    # ---- forget loops ----------------------------------------------------------------------------------
+    def forget(self, n_iters: int, forget_loss_fn: LossFn, remain_loss_fn: LossFn, *, use_mask: bool = True,
+               forget_alpha: float = 1.0, remain_alpha: float = 1.0, decay_forget_alpha: bool = False,
+               mask_order: str = "mask_then_clip", log_every: int = 0) -> None:
+        """method "ron": forget step (mask, clip, step) then remain step (clip?, step) then EMA, every
+        iteration (runners/diffusion.py:1075-1180; DiT/forget.py:256-322; nsfw_removal.py:108-173).
+        The closures return the UNWEIGHTED losses (-loss for gradient ascent)."""
+        mhp, cfg = self.mhp, self.cfg
+        mhp.zero_grad()
+        self.model.train()
+        for step in range(n_iters):
+            alpha = cosine_lr_scheduler(forget_alpha, step, n_iters) if decay_forget_alpha else forget_alpha
+            (alpha * forget_loss_fn(step)).backward()
+            mhp.forget_step(use_mask=use_mask, max_norm=cfg.clip_forget, mask_order=mask_order)
+            (remain_alpha * remain_loss_fn(step)).backward()
+            mhp.remain_step(max_norm=cfg.clip_remain, ema=True)
+            if log_every and (step + 1) % log_every == 0:
+                print(f"step:{step:04d} forget a:{alpha:.8f}")
+
+    # ---- checkpoints -------------------------------------------------------------------------------
+    def checkpoint(self, step: int = 0, args=None):
+        """DDPM: [model_sd, opt_sd, step, ema_shadow]; DiT: {model, ema, opt, args}; SD: state_dict."""
+        pre = self.cfg.key_prefix
+        model_sd = {pre + k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        if self.family == "ddpm":
+            shadow = {k[len(pre):]: v for k, v in self.mhp.slow_state_dict().items()}   # EMAHelper keys are module-local
+            return formats.ddpm_checkpoint(model_sd, self.mhp.optimizer_state_dict(), step, shadow)
+        if self.family == "dit":
+            ema_sd = {k[len(pre):]: v for k, v in self.mhp.slow_state_dict().items()}     # ema = deepcopy(model): bare names
+            return formats.dit_checkpoint(model_sd, ema_sd, self.mhp.optimizer_state_dict(), args)
+        return {k: v.detach().clone() for k, v in self.model.state_dict().items()}
