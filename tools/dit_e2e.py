@@ -1,0 +1,215 @@
+#!/usr/bin/env python
+"""End-to-end DiT-XL/2 unlearning steps/s on B200 (BASELINE.json: "DiT-XL/2 unlearn steps/s").
+
+Model forward/backward in PyTorch (tools/dit_xl2.py harness, TF32 matmuls as DiT/forget.py:6-8),
+synthetic 4x32x32 latents, random-init weights.  Two arms on the SAME GPU:
+
+  stock : the reference's loop as written — DiT/forget.py:285-322 for the forget loop
+          (per-parameter `grad *= mask[name].to(device)`, clip_grad_norm_, AdamW.step, update_ema)
+          and DiT/generate_fisher.py:232-239 for the Fisher loop (`F[name] += grad.cpu()**2 / n`).
+          `--mask-on-device` is a best-effort variant with the mask uploaded once.
+  ours  : the same iterations with everything after backward done by the flat-vector kernels.
+
+Single GPU: `python tools/dit_e2e.py`.  N GPUs (ours only; the reference's DataParallel is
+single-process): `python -m torch.distributed.run --nproc-per-node N ... tools/dit_e2e.py --arm ours`
+— data parallel, gradient all-reduce over NCCL, sharded update, weight all-gather.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+from copy import deepcopy
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+from dit_xl2 import DiTXL2Harness, synthetic_loss  # noqa: E402
+
+
+def make_batch(bs, dev, gen, forget_class=207):
+    x = torch.randn(bs, 4, 32, 32, device=dev, generator=gen)
+    t = torch.randint(0, 1000, (bs,), device=dev, generator=gen)
+    noise = torch.randn(bs, 4, 32, 32, device=dev, generator=gen)
+    y_f = torch.full((bs,), forget_class, device=dev)
+    y_r = torch.randint(0, 1000, (bs,), device=dev, generator=gen)
+    return x, t, noise, y_f, y_r
+
+
+def timed(fn, steps, warmup, sync):
+    for i in range(warmup):
+        fn(i)
+    sync()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        fn(warmup + i)
+    sync()
+    return (time.perf_counter() - t0) / steps
+
+
+def run_stock(args, dev, ac):
+    torch.manual_seed(0)
+    model = DiTXL2Harness().to(dev)
+    ema = deepcopy(model)
+    for p in ema.parameters():
+        p.requires_grad = False
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    cg = torch.Generator().manual_seed(2)
+    mask = {n: (torch.rand(p.shape, generator=cg) < 0.5) if p.requires_grad else 0
+            for n, p in model.named_parameters()}              # what torch.load(mask_path) returns: CPU bools
+    if args.mask_on_device:
+        mask = {n: (m.to(dev) if torch.is_tensor(m) else m) for n, m in mask.items()}
+    model.train()
+    res = {}
+
+    def forget_iter(i):
+        x, t, noise, y_f, y_r = make_batch(args.batch_size, dev, gen)
+        loss = -synthetic_loss(model, x, t, y_f, noise, ac)
+        opt.zero_grad()
+        (args.forget_alpha * loss).backward()
+        for name, param in model.named_parameters():
+            if param.grad is not None:
+                param.grad *= mask[name].to(param.grad.device)
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        loss = synthetic_loss(model, x, t, y_r, noise, ac)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        with torch.no_grad():
+            for (_, pe), (_, pm) in zip(ema.named_parameters(), model.named_parameters()):
+                pe.mul_(0.9999).add_(pm.data, alpha=1 - 0.9999)
+
+    res["forget_s_per_it"] = timed(forget_iter, args.steps, args.warmup, torch.cuda.synchronize)
+
+    fisher = {n: 0 for n, _ in model.named_parameters()}
+
+    def fisher_iter(i):
+        x, t, noise, y_f, _ = make_batch(args.batch_size, dev, gen)
+        loss = synthetic_loss(model, x, t, y_f, noise, ac)
+        opt.zero_grad()
+        loss.backward()
+        with torch.no_grad():
+            for name, param in model.named_parameters():
+                if param.grad is not None:
+                    fisher[name] += (param.grad.data.cpu() ** 2) / 2000
+
+    res["fisher_s_per_it"] = timed(fisher_iter, max(2, args.steps // 4), 1, torch.cuda.synchronize)
+    return res
+
+
+def run_ours(args, dev, ac, rank, world):
+    import sfron_b200 as sfr
+    torch.manual_seed(0)
+    model = DiTXL2Harness().to(dev)
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+    opt = sfr.OptConfig(kind="adamw", lr=1e-4, weight_decay=0.0)
+    flat = sfr.FlatParams(model, dev)
+    if world > 1:
+        import torch.distributed as dist
+        from sfron_b200.dist import ShardGroup, ShardedHotPath
+        sg = ShardGroup(flat.n)
+        hp = ShardedHotPath(sg, dev, opt, ema_mode="dit", ema_a=0.9999)
+        lo, hi = sg.lo, sg.hi
+    else:
+        sg = None
+        hp = sfr.HotPath(flat.n, dev, opt, ema_mode="dit", ema_a=0.9999)
+        lo, hi = 0, flat.n
+    p_loc = flat.p[lo:hi]
+    hp.init_slow(p_loc)
+    frozen_slow = flat.frozen.clone()
+    hp.mask.copy_((torch.rand(hi - lo, device=dev, generator=gen) < 0.5).to(torch.uint8))
+    model.train()
+    res = {}
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def grads():
+        if sg is not None:
+            return sg.reduce_gradients_(flat.g, average=True)
+        return flat.g
+
+    def forget_iter(i):
+        x, t, noise, y_f, y_r = make_batch(args.batch_size, dev, gen)
+        (args.forget_alpha * -synthetic_loss(model, x, t, y_f, noise, ac)).backward()
+        # single GPU: the update kernel zeroes g on its way out (fused optimizer.zero_grad());
+        # sharded: each rank only rewrites its slice, so the full local gradient is memset
+        hp.forget_step(p_loc, grads(), max_norm=1.0, zero_grad=sg is None)
+        if sg is not None:
+            sg.all_gather_params_(flat.p)
+            flat.g.zero_()
+        synthetic_loss(model, x, t, y_r, noise, ac).backward()
+        hp.remain_step(p_loc, grads(), ema=True, zero_grad=sg is None)
+        hp.ema_only(flat.frozen, frozen_slow)
+        if sg is not None:
+            sg.all_gather_params_(flat.p)
+            flat.g.zero_()
+
+    flat.g.zero_()
+    res["forget_s_per_it"] = timed(forget_iter, args.steps, args.warmup, sync)
+
+    def fisher_iter(i):
+        x, t, noise, y_f, _ = make_batch(args.batch_size, dev, gen)
+        synthetic_loss(model, x, t, y_f, noise, ac).backward()
+        hp.fisher_accumulate("forget", grads(), 2000.0)
+        flat.g.zero_()
+
+    res["fisher_s_per_it"] = timed(fisher_iter, args.steps, args.warmup, sync)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--arm", default="both", choices=["both", "stock", "ours"])
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch-size", type=int, default=1, help="per GPU (DiT/forget.py default 1)")
+    ap.add_argument("--forget-alpha", type=float, default=1e-3)
+    ap.add_argument("--mask-on-device", action="store_true")
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.backends.cuda.matmul.allow_tf32 = True       # DiT/forget.py:6-8
+    torch.backends.cudnn.allow_tf32 = True
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    betas = torch.linspace(1e-4, 0.02, 1000, dtype=torch.float64)
+    ac = torch.cumprod(1 - betas, 0).float().to(dev)
+    out = {"model": "DiT-XL/2 harness, 675,129,632 params, random init", "batch_size_per_gpu": args.batch_size,
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "tf32": True}
+    if args.arm in ("both", "stock") and world == 1:
+        r = run_stock(args, dev, ac)
+        out["stock" + ("_mask_on_device" if args.mask_on_device else "")] = {
+            "forget_steps_per_s": 1 / r["forget_s_per_it"], "fisher_steps_per_s": 1 / r["fisher_s_per_it"]}
+        torch.cuda.empty_cache()
+    if args.arm in ("both", "ours"):
+        r = run_ours(args, dev, ac, rank, world)
+        out["ours"] = {"forget_steps_per_s": 1 / r["forget_s_per_it"], "fisher_steps_per_s": 1 / r["fisher_s_per_it"],
+                       "global_batch": args.batch_size * world}
+    if rank == 0:
+        line = json.dumps(out)
+        print(line, flush=True)
+        if args.out:
+            with open(args.out, "a") as f:
+                f.write(line + "\n")
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
