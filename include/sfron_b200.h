@@ -154,13 +154,17 @@ typedef struct sfr_select_state {
 
 SFR_API int sfr_select_init(sfr_select_state* state_dev, unsigned long long* bins_dev,
                     unsigned long long k, sfr_stream_t stream);
+/* scratch_dev (>= sfr_select_scratch_elems(n) u64) is required for pass 1, which stages the keys
+ * matching the chosen prefix there for the tie handling of sfr_select_apply; unused by pass 0. */
 SFR_API int sfr_select_hist(const float* a, const float* b, int key_mode, float eps,
                     int64_t n, int pass, const sfr_select_state* state_dev,
-                    unsigned long long* bins_dev, sfr_stream_t stream);
+                    unsigned long long* bins_dev, unsigned long long* scratch_dev,
+                    sfr_stream_t stream);
 SFR_API int sfr_select_scan(int pass, sfr_select_state* state_dev,
                     unsigned long long* bins_dev, sfr_stream_t stream);
-/* tie_base_dev: device u64 (NULL = 0).  scratch_dev: device u64 array of at least
- * sfr_select_scratch_elems(n) elements (used only when ties must be ordered). */
+/* tie_base_dev: device u64 (NULL = 0).  scratch_dev: the SAME device u64 array of at least
+ * sfr_select_scratch_elems(n) elements that pass 1 filled (per-chunk tie counts, their scan, and
+ * the staged candidates; read only when ties must be ordered). */
 SFR_API int64_t sfr_select_scratch_elems(int64_t n);
 SFR_API int sfr_select_apply(const float* a, const float* b, int key_mode, float eps,
                      int64_t n, const sfr_select_state* state_dev,

@@ -138,9 +138,9 @@ def main():
             capi.select_hist(g32, None, capi.KEY_ABS, 0, state, bins)
             capi.select_scan(0, state, bins)
             emit("topk_hist_pass1", n, "-", 4,
-                 timer(lambda: capi.select_hist(g32, None, capi.KEY_ABS, 1, state, bins)))
+                 timer(lambda: capi.select_hist(g32, None, capi.KEY_ABS, 1, state, bins, scratch)))
             bins.zero_()
-            capi.select_hist(g32, None, capi.KEY_ABS, 1, state, bins)
+            capi.select_hist(g32, None, capi.KEY_ABS, 1, state, bins, scratch)
             capi.select_scan(1, state, bins)
             emit("topk_apply", n, "-", 5,
                  timer(lambda: capi.select_apply(g32, None, capi.KEY_ABS, state, None, scratch, topk)))

@@ -97,7 +97,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.sfr_select_init.restype = C.c_int
     lib.sfr_select_init.argtypes = [vp, vp, u64, vp]
     lib.sfr_select_hist.restype = C.c_int
-    lib.sfr_select_hist.argtypes = [vp, vp, C.c_int, f32, i64, C.c_int, vp, vp, vp]
+    lib.sfr_select_hist.argtypes = [vp, vp, C.c_int, f32, i64, C.c_int, vp, vp, vp, vp]
     lib.sfr_select_scan.restype = C.c_int
     lib.sfr_select_scan.argtypes = [C.c_int, vp, vp, vp]
     lib.sfr_select_scratch_elems.restype = i64
@@ -211,10 +211,14 @@ def select_init(state: torch.Tensor, bins: torch.Tensor, k: int) -> None:
 
 
 def select_hist(a: torch.Tensor, b: Optional[torch.Tensor], key_mode: int, pass_: int,
-                state: torch.Tensor, bins: torch.Tensor, eps: float = 1e-15) -> None:
+                state: torch.Tensor, bins: torch.Tensor, scratch: Optional[torch.Tensor] = None,
+                eps: float = 1e-15) -> None:
+    if scratch is not None and scratch.numel() < select_scratch_elems(a.numel()):
+        raise SfrError(ERR_ARG, "select_hist", "scratch too small")
     _check(load().sfr_select_hist(_ptr(a, torch.float32, "a"), _ptr(b, torch.float32, "b"), key_mode,
                                   float(eps), a.numel(), pass_, _ptr(state, torch.int64, "state"),
-                                  _ptr(bins, torch.int64, "bins"), _stream()), "sfr_select_hist")
+                                  _ptr(bins, torch.int64, "bins"), _ptr(scratch, torch.int64, "scratch"),
+                                  _stream()), "sfr_select_hist")
 
 
 def select_scan(pass_: int, state: torch.Tensor, bins: torch.Tensor) -> None:

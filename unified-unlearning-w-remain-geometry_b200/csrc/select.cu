@@ -110,17 +110,65 @@ select_hist0_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
   }
 }
 
+// ---- scratch layout (unsigned long long words) ------------------------------------------------
+//   [0, nchunks)                  per-chunk count of threshold-equal keys
+//   [nchunks, 2*nchunks)          exclusive scan of those counts (+ tie_base)
+//   header (kCandHeader words):   [0] overflow flag, [1] number of regions, [2] region capacity,
+//                                 [8 + r] entries staged in region r
+//   candidate regions             cand_cap words: (flat index << 16) | key[15:0]
+constexpr int64_t kChunkElems = 8192;       // == kChunk below (kApplyThreads * 4 * kChunkVecs)
+constexpr int kMaxRegions = 2048;           // >= CTAs of the pass-1 grid
+constexpr int kCandHeader = 8 + kMaxRegions;
+
+__host__ __device__ inline int64_t scratch_nchunks(int64_t n) { return (n + kChunkElems - 1) / kChunkElems; }
+__host__ __device__ inline int64_t scratch_cand_cap(int64_t n) {
+  const int64_t byfrac = n / 32;            // room for 3 % of the elements sharing the 15-bit prefix
+  const int64_t floor_ = (int64_t)kMaxRegions * 64;
+  return byfrac > floor_ ? byfrac : floor_;
+}
+
 // ---- pass 1: filtered 16-bit histogram straight into global bins -----------------------------
+// Keys whose bits [30:16] equal the chosen prefix (typically < 1 % of the elements) are also
+// STAGED — (flat index, low 16 key bits) — in a region private to the CTA (one shared-memory
+// counter, no global atomics).  The ordered-tie apply later counts threshold-equal keys per chunk
+// from this short list instead of re-reading the whole vector; if any region overflows (degenerate
+// inputs: most keys equal) a flag makes the apply fall back to the streaming count.
 constexpr int kFiltThreads = 256;
 constexpr int kFiltCtasPerSm = 4;
 constexpr int kFiltUnroll = 4;
+
+struct CandStage {
+  unsigned long long* region;
+  unsigned int cap;
+  unsigned int* s_count;
+  unsigned int* s_over;
+  __device__ __forceinline__ void push(int64_t idx, uint32_t key) {
+    if (*reinterpret_cast<volatile unsigned int*>(s_over)) return;
+    const unsigned int pos = atomicAdd(s_count, 1u);
+    if (pos < cap) region[pos] = ((unsigned long long)idx << 16) | (key & 0xffffu);
+    else *reinterpret_cast<volatile unsigned int*>(s_over) = 1u;
+  }
+};
 
 template <int MODE>
 __global__ void __launch_bounds__(kFiltThreads, kFiltCtasPerSm)
 select_hist1_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps, int64_t n,
                     const sfr_select_state* __restrict__ state,
-                    unsigned long long* __restrict__ bins) {
+                    unsigned long long* __restrict__ bins, unsigned long long* __restrict__ scratch) {
   if (state->select_none || state->select_all) return;
+  __shared__ unsigned int s_count, s_over;
+  if (threadIdx.x == 0) {
+    s_count = 0;
+    s_over = 0;
+  }
+  __syncthreads();
+  unsigned long long* hdr = scratch + 2 * scratch_nchunks(n);
+  CandStage cs;
+  cs.cap = (unsigned int)(scratch_cand_cap(n) / gridDim.x);
+  cs.region = hdr + kCandHeader + (int64_t)blockIdx.x * cs.cap;
+  cs.s_count = &s_count;
+  cs.s_over = &s_over;
+
   const uint32_t prefix = state->prefix;
   const int64_t nvec = n >> 2;
   const int64_t tile = (int64_t)kFiltThreads * kFiltUnroll;
@@ -150,19 +198,28 @@ select_hist1_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
       const uint32_t k1 = key_from<MODE>(x[u].y, y[u].y, eps);
       const uint32_t k2 = key_from<MODE>(x[u].z, y[u].z, eps);
       const uint32_t k3 = key_from<MODE>(x[u].w, y[u].w, eps);
-      if ((k0 >> 16) == prefix) rc.push(bins, k0 & 0xffffu);
-      if ((k1 >> 16) == prefix) rc.push(bins, k1 & 0xffffu);
-      if ((k2 >> 16) == prefix) rc.push(bins, k2 & 0xffffu);
-      if ((k3 >> 16) == prefix) rc.push(bins, k3 & 0xffffu);
+      if ((k0 >> 16) == prefix) { rc.push(bins, k0 & 0xffffu); cs.push(v * 4 + 0, k0); }
+      if ((k1 >> 16) == prefix) { rc.push(bins, k1 & 0xffffu); cs.push(v * 4 + 1, k1); }
+      if ((k2 >> 16) == prefix) { rc.push(bins, k2 & 0xffffu); cs.push(v * 4 + 2, k2); }
+      if ((k3 >> 16) == prefix) { rc.push(bins, k3 & 0xffffu); cs.push(v * 4 + 3, k3); }
     }
   }
   const int64_t tail0 = nvec << 2;
   if (blockIdx.x == 0 && threadIdx.x < (n - tail0)) {
     const int64_t i = tail0 + threadIdx.x;
     const uint32_t k = key_from<MODE>(a[i], MODE == SFR_KEY_RATIO ? b[i] : 0.f, eps);
-    if ((k >> 16) == prefix) rc.push(bins, k & 0xffffu);
+    if ((k >> 16) == prefix) { rc.push(bins, k & 0xffffu); cs.push(i, k); }
   }
   rc.flush(bins);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    hdr[8 + blockIdx.x] = s_count < cs.cap ? s_count : cs.cap;
+    if (s_over) hdr[0] = 1ull;
+    if (blockIdx.x == 0) {
+      hdr[1] = gridDim.x;
+      hdr[2] = cs.cap;
+    }
+  }
 }
 
 // ---- scans (one CTA) -----------------------------------------------------------------------
@@ -170,50 +227,67 @@ constexpr int kScanThreads = 1024;
 
 // Finds the largest bin B with  above(B) < want <= above(B) + bins[B], scanning from the top.
 // Returns (B, above(B)) to every thread through shared memory; B = -1 if want > total.
+// Thread t owns kPer consecutive bins (descending); all kPer loads are issued before the first
+// add, thread sums are scanned with warp shuffles (one barrier pair for the 32 warp totals).
+// (Keeping the kPer counters in registers would spill at 1024 threads; the one thread that holds
+// the crossing re-reads its bins instead.)
 template <int NBINS>
 __device__ void find_bin_from_top(const unsigned long long* __restrict__ bins,
                                   unsigned long long want, int* out_bin,
                                   unsigned long long* out_above, unsigned long long* out_total) {
   constexpr int kPer = NBINS / kScanThreads;
-  __shared__ unsigned long long part[kScanThreads];
+  __shared__ unsigned long long warp_tot[32];
   __shared__ int s_bin;
-  __shared__ unsigned long long s_above;
-  // thread t owns the bins [hi - kPer + 1, hi] with hi = NBINS-1 - t*kPer (descending order)
+  __shared__ unsigned long long s_above, s_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hi = NBINS - 1 - (int)threadIdx.x * kPer;
   unsigned long long mine = 0;
-#pragma unroll 4
-  for (int j = 0; j < kPer; ++j) mine += bins[hi - j];
-  part[threadIdx.x] = mine;
+#pragma unroll 8
+  for (int j = 0; j < kPer; ++j) mine += bins[hi - j];  // 8 independent loads in flight
   if (threadIdx.x == 0) {
     s_bin = -1;
     s_above = 0;
   }
-  __syncthreads();
-  // inclusive scan over threads (Hillis-Steele; 1024 entries, 10 steps)
-  for (int off = 1; off < kScanThreads; off <<= 1) {
-    unsigned long long add = threadIdx.x >= off ? part[threadIdx.x - off] : 0ull;
-    __syncthreads();
-    part[threadIdx.x] += add;
-    __syncthreads();
+  unsigned long long incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long up = __shfl_up_sync(kFullMask, incl, o);
+    if (lane >= o) incl += up;
   }
-  const unsigned long long incl = part[threadIdx.x];
-  const unsigned long long excl = incl - mine;
-  if (want > excl && want <= incl) {  // exactly one thread
-    unsigned long long above = excl;
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = warp_tot[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long up = __shfl_up_sync(kFullMask, wi, o);
+      if (lane >= o) wi += up;
+    }
+    warp_tot[lane] = wi - w;  // exclusive prefix of the warp totals
+    if (lane == 31) s_total = wi;
+  }
+  __syncthreads();
+  const unsigned long long excl = warp_tot[warp] + (incl - mine);
+  if (want > excl && want <= excl + mine) {  // exactly one thread
+    // re-read this thread's bins (L2-resident) with independent loads; no dependent branches
+    unsigned long long above = excl, found_above = 0;
+    int found = -1;
+#pragma unroll 8
     for (int j = 0; j < kPer; ++j) {
       const unsigned long long c = bins[hi - j];
-      if (want <= above + c) {
-        s_bin = hi - j;
-        s_above = above;
-        break;
+      if (found < 0 && want <= above + c) {
+        found = hi - j;
+        found_above = above;
       }
       above += c;
     }
+    s_bin = found;
+    s_above = found_above;
   }
   __syncthreads();
   *out_bin = s_bin;
   *out_above = s_above;
-  *out_total = part[kScanThreads - 1];
+  *out_total = s_total;
   __syncthreads();
 }
 
@@ -263,6 +337,7 @@ select_scan_kernel(int pass, sfr_select_state* __restrict__ state,
 constexpr int kApplyThreads = 256;
 constexpr int kChunkVecs = 8;                            // float4 per thread per chunk
 constexpr int64_t kChunk = (int64_t)kApplyThreads * 4 * kChunkVecs;  // 8192 elements
+static_assert(kChunk == kChunkElems, "scratch layout and apply kernels must agree on the chunk size");
 
 __device__ __forceinline__ bool ties_need_order(const sfr_select_state* s) {
   return !s->select_none && !s->select_all && s->tie_budget != s->count_eq;
@@ -313,9 +388,10 @@ select_tie_count_kernel(const float* __restrict__ a, const float* __restrict__ b
                         int64_t n, const sfr_select_state* __restrict__ state,
                         unsigned long long* __restrict__ scratch) {
   if (!ties_need_order(state)) return;
+  const int64_t nchunks = (n + kChunk - 1) / kChunk;
+  if (scratch[2 * nchunks] == 0ull) return;  // candidates did not overflow: counted from the list
   __shared__ unsigned int red[32];
   const uint32_t thr = state->thr_key;
-  const int64_t nchunks = (n + kChunk - 1) / kChunk;
   for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
     uint32_t key[kChunkVecs][4], valid;
     load_chunk_keys<MODE>(a, b, eps, n, c * kChunk, key, valid);
@@ -330,30 +406,78 @@ select_tie_count_kernel(const float* __restrict__ a, const float* __restrict__ b
   }
 }
 
+// Per-chunk tie counts from the staged candidates (the usual path): every region is scanned by
+// one CTA; only entries whose low key bits equal the threshold's touch a (zeroed) chunk counter.
+__global__ void __launch_bounds__(256, 8)
+select_tie_count_candidates_kernel(int64_t n, const sfr_select_state* __restrict__ state,
+                                   unsigned long long* __restrict__ scratch) {
+  if (!ties_need_order(state)) return;
+  const int64_t nchunks = (n + kChunk - 1) / kChunk;
+  const unsigned long long* hdr = scratch + 2 * nchunks;
+  if (hdr[0] != 0ull) return;  // overflow: the streaming kernel counts instead
+  const unsigned int thr16 = state->thr_key & 0xffffu;
+  const int regions = (int)hdr[1];
+  const unsigned long long cap = hdr[2];
+  for (int r = blockIdx.x; r < regions; r += gridDim.x) {
+    const unsigned long long* region = hdr + kCandHeader + (unsigned long long)r * cap;
+    const unsigned int cnt = (unsigned int)hdr[8 + r];
+    for (unsigned int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const unsigned long long e = region[i];
+      if ((unsigned int)(e & 0xffffull) == thr16) atomicAdd(scratch + (e >> 16) / kChunk, 1ull);
+    }
+  }
+}
+
+// Exclusive scan of the per-chunk tie counts by ONE CTA: 16 consecutive counters per thread,
+// warp-shuffle scan of the per-thread sums, 32 warp totals through shared memory — two barriers per
+// 16384 counters (82 k chunks at DiT-XL/2 size = 6 iterations).
+constexpr int kScanItems = 16;
+
 __global__ void __launch_bounds__(1024, 1)
 select_tie_scan_kernel(int64_t nchunks, const sfr_select_state* __restrict__ state,
                        const unsigned long long* __restrict__ tie_base,
                        unsigned long long* __restrict__ scratch) {
   if (!ties_need_order(state)) return;
-  __shared__ unsigned long long part[1024];
-  __shared__ unsigned long long carry;
-  if (threadIdx.x == 0) carry = tie_base ? *tie_base : 0ull;
-  __syncthreads();
-  for (int64_t base = 0; base < nchunks; base += 1024) {
-    const int64_t i = base + threadIdx.x;
-    const unsigned long long mine = i < nchunks ? scratch[i] : 0ull;
-    part[threadIdx.x] = mine;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-      unsigned long long add = threadIdx.x >= off ? part[threadIdx.x - off] : 0ull;
-      __syncthreads();
-      part[threadIdx.x] += add;
-      __syncthreads();
+  __shared__ unsigned long long warp_tot[32];
+  __shared__ unsigned long long carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long carry = tie_base ? *tie_base : 0ull;
+  const int64_t tile = (int64_t)1024 * kScanItems;
+  for (int64_t base = 0; base < nchunks; base += tile) {
+    const int64_t i0 = base + (int64_t)threadIdx.x * kScanItems;
+    unsigned long long v[kScanItems], mine = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      v[j] = i0 + j < nchunks ? scratch[i0 + j] : 0ull;
+      mine += v[j];
     }
-    if (i < nchunks) scratch[nchunks + i] = carry + part[threadIdx.x] - mine;  // exclusive
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long up = __shfl_up_sync(kFullMask, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) carry += part[1023];
+    if (warp == 0) {
+      unsigned long long w = warp_tot[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(kFullMask, wi, o);
+        if (lane >= o) wi += up;
+      }
+      warp_tot[lane] = wi - w;              // exclusive prefix of the warp totals
+      if (lane == 31) carry_s = wi;          // tile total
+    }
     __syncthreads();
+    unsigned long long run = carry + warp_tot[warp] + (incl - mine);
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      if (i0 + j < nchunks) scratch[nchunks + i0 + j] = run;
+      run += v[j];
+    }
+    carry += carry_s;
+    __syncthreads();                         // warp_tot / carry_s reused by the next tile
   }
 }
 
@@ -424,16 +548,34 @@ select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
     const int64_t base = c * kChunk;
     const unsigned long long chunk_ties = scratch[c];        // uniform over the CTA
     unsigned long long run = scratch[nchunks + c];           // ties before this chunk
+    if (chunk_ties == 0 && base + kChunk <= n) {
+      // tie-free full chunk (almost all of them): straight-line stream, mask = key > thr
+      float4 x[kChunkVecs], y[kChunkVecs];
+#pragma unroll
+      for (int sl = 0; sl < kChunkVecs; ++sl) {
+        const int64_t e0 = base + ((int64_t)sl * kApplyThreads + threadIdx.x) * 4;
+        x[sl] = ld_stream(reinterpret_cast<const float4*>(a + e0));
+        if constexpr (MODE == SFR_KEY_RATIO) y[sl] = ld_stream(reinterpret_cast<const float4*>(b + e0));
+        else y[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int sl = 0; sl < kChunkVecs; ++sl) {
+        const int64_t e0 = base + ((int64_t)sl * kApplyThreads + threadIdx.x) * 4;
+        const uint32_t s0 = key_from<MODE>(x[sl].x, y[sl].x, eps) > thr;
+        const uint32_t s1 = key_from<MODE>(x[sl].y, y[sl].y, eps) > thr;
+        const uint32_t s2 = key_from<MODE>(x[sl].z, y[sl].z, eps) > thr;
+        const uint32_t s3 = key_from<MODE>(x[sl].w, y[sl].w, eps) > thr;
+        __stcs(reinterpret_cast<unsigned int*>(mask + e0), s0 | (s1 << 8) | (s2 << 16) | (s3 << 24));
+      }
+      continue;
+    }
     uint32_t key[kChunkVecs][4], valid;
     load_chunk_keys<MODE>(a, b, eps, n, base, key, valid);
 #pragma unroll
     for (int sl = 0; sl < kChunkVecs; ++sl) {
       const int64_t e0 = base + ((int64_t)sl * kApplyThreads + threadIdx.x) * 4;
       uint32_t sel[4];
-      if (chunk_ties == 0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) sel[q] = key[sl][q] > thr;
-      } else {
+      {
         unsigned int tq[4], mine = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -503,7 +645,8 @@ extern "C" int sfr_select_init(sfr_select_state* state, unsigned long long* bins
 
 extern "C" int sfr_select_hist(const float* a, const float* b, int key_mode, float eps,
                                int64_t n, int pass, const sfr_select_state* state,
-                               unsigned long long* bins, sfr_stream_t stream) {
+                               unsigned long long* bins, unsigned long long* scratch,
+                               sfr_stream_t stream) {
   using namespace sfr;
   if (n < 0 || (pass != 0 && pass != 1)) return SFR_ERR_ARG;
   if (key_mode != SFR_KEY_ABS && key_mode != SFR_KEY_RATIO) return SFR_ERR_ARG;
@@ -531,9 +674,13 @@ extern "C" int sfr_select_hist(const float* a, const float* b, int key_mode, flo
     else select_hist0_kernel<SFR_KEY_RATIO><<<grid, kHistThreads, smem, s>>>(a, b, eps, n, bins);
   } else {
     const int64_t tile = (int64_t)kFiltThreads * kFiltUnroll;
-    const int grid = persistent_grid((nvec + tile - 1) / tile, kFiltCtasPerSm);
-    if (key_mode == SFR_KEY_ABS) select_hist1_kernel<SFR_KEY_ABS><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins);
-    else select_hist1_kernel<SFR_KEY_RATIO><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins);
+    SFR_REQUIRE_PTR(scratch);
+    int grid = persistent_grid((nvec + tile - 1) / tile, kFiltCtasPerSm);
+    if (grid > kMaxRegions) grid = kMaxRegions;
+    // zero the per-chunk tie counters and the candidate header (the regions need no clearing)
+    cudaMemsetAsync(scratch, 0, (size_t)(2 * scratch_nchunks(n) + kCandHeader) * sizeof(unsigned long long), s);
+    if (key_mode == SFR_KEY_ABS) select_hist1_kernel<SFR_KEY_ABS><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins, scratch);
+    else select_hist1_kernel<SFR_KEY_RATIO><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins, scratch);
   }
   SFR_LAUNCH_STATUS();
 }
@@ -550,8 +697,9 @@ extern "C" int sfr_select_scan(int pass, sfr_select_state* state, unsigned long 
 }
 
 extern "C" int64_t sfr_select_scratch_elems(int64_t n) {
-  if (n <= 0) return 2;
-  return 2 * ((n + sfr::kChunk - 1) / sfr::kChunk);  // per-chunk tie counts + their exclusive scan
+  if (n < 0) n = 0;
+  // per-chunk tie counts + their exclusive scan + candidate header + candidate regions
+  return 2 * sfr::scratch_nchunks(n) + sfr::kCandHeader + sfr::scratch_cand_cap(n);
 }
 
 extern "C" int sfr_select_apply(const float* a, const float* b, int key_mode, float eps,
@@ -577,6 +725,9 @@ extern "C" int sfr_select_apply(const float* a, const float* b, int key_mode, fl
   const int grid = persistent_grid(nchunks, 8);
   const int64_t stile = (int64_t)kApplyThreads * kApplyUnroll;
   const int sgrid = persistent_grid(((n >> 2) + stile - 1) / stile, 4);
+  // the per-chunk counters are accumulated into: clear them here so that apply is idempotent
+  cudaMemsetAsync(scratch, 0, (size_t)nchunks * sizeof(unsigned long long), s);
+  select_tie_count_candidates_kernel<<<persistent_grid(kMaxRegions, 8), 256, 0, s>>>(n, state, scratch);
   if (key_mode == SFR_KEY_ABS) {
     select_tie_count_kernel<SFR_KEY_ABS><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch);
     select_tie_scan_kernel<<<1, 1024, 0, s>>>(nchunks, state, tie_base, scratch);

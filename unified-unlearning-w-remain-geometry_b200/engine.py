@@ -166,10 +166,10 @@ class HotPath:
         state, bins, scratch = self._select_buffers()
         mask = self.mask if out is None else out
         capi.select_init(state, bins, k)
-        capi.select_hist(values, other, mode, 0, state, bins, eps)
+        capi.select_hist(values, other, mode, 0, state, bins, None, eps)
         self.reduce_bins_(bins, capi.SELECT_BINS0)
         capi.select_scan(0, state, bins)
-        capi.select_hist(values, other, mode, 1, state, bins, eps)
+        capi.select_hist(values, other, mode, 1, state, bins, scratch, eps)
         local_bins = self.keep_local_bins_(bins)
         self.reduce_bins_(bins, capi.SELECT_BINS1)
         capi.select_scan(1, state, bins)
