@@ -340,8 +340,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic", type=float, default=None,
-                    help="dram bytes per launch of the dominant kernel from the committed ncu capture")
+                    help="dram bytes per launch of the dominant kernel (default: the committed ncu capture "
+                         "profiles/r1_ncu_full_fused_update_n675M_raw.csv when --elems is the default)")
     args = ap.parse_args()
+    if args.traffic is None and args.elems == N3:
+        # ncu --set full, fused_update_kernel<AdamW,EMA_DIT,f32> at n = N3: dram__bytes_read.sum 13.502762 GB
+        # + dram__bytes_write.sum 10.747480 GB per launch (algorithmic: 36 B x N3 = 24.305 GB)
+        args.traffic = 13.502762e9 + 10.747480e9
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                  # timing rule: W >= 3
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -65,7 +65,13 @@ def main():
     sg.all_gather_params_(p)
     if rank == 0:
         ref = O.FlatReferenceLoop({"w": (n,)}, {"w": theta0}, "adam", dict(lr=1e-4), ema_mode="ddpm", ema_a=1e-4)
-        g_mean = torch.stack(gf_all).sum(0) / world
+        # The oracle gets the gradient AS ALL-REDUCED (every rank holds the full mean after the
+        # all-reduce).  The order in which a collective sums 4+ ranks is not the order of a sequential
+        # CPU sum; where the mean cancels to ~1e-9 that last-bit difference is amplified by Adam's
+        # normalisation to ~5e-6 of the weight — measured with the CPU oracle ALONE by only changing the
+        # summation order (8 of 3 M elements).  It is a property of data-parallel reduction (the
+        # reference's DataParallel reduce_add has its own order too), not of the sharded update.
+        g_mean = g_local.cpu()
         ref.forget_step({"w": g_mean}, mask={"w": ref_mask}, max_norm=1.0)
         ref.remain_step({"w": gr}, max_norm=1.0, ema=True)
         a, b = p.cpu().double(), ref.flat("p").double()
