@@ -357,6 +357,8 @@ def main():
         return
     if world > 1:
         import torch.distributed as dist
+        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
+        os.environ["NCCL_DEBUG"] = os.environ.get("SFR_NCCL_DEBUG", "WARN")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
