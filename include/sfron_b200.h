@@ -118,6 +118,7 @@ SFR_API int sfr_ratio_mask_multi(const float* ff, const float* rf, int64_t n,
  * is never selected, as in torch's ascending sort of -|x|).
  *   SFR_KEY_ABS   : x = a[i]                       (b ignored)
  *   SFR_KEY_RATIO : x = (a[i] + eps) / (b[i] + eps)  (top-k by Fisher ratio; extension)
+ *   SFR_KEY_ABSDIFF: x = a[i] - b[i]                 (SD/train-scripts/proximal_gradient.py:158-159)
  *
  * Protocol (all on one stream, no host synchronisation needed):
  *   memset(state, 0), state->k = k                      (sfr_select_init)
@@ -136,6 +137,7 @@ SFR_API int sfr_ratio_mask_multi(const float* ff, const float* rf, int64_t n,
  * ======================================================================== */
 #define SFR_KEY_ABS 0
 #define SFR_KEY_RATIO 1
+#define SFR_KEY_ABSDIFF 2 /* x = a[i] - b[i]  (proximal gradient: |theta - theta0|) */
 #define SFR_SELECT_BINS0 32768 /* key bits [30:16] */
 #define SFR_SELECT_BINS1 65536 /* key bits [15:0]  */
 
@@ -241,6 +243,26 @@ SFR_API int sfr_fused_update(float* p, void* g, float* m, float* v, const uint8_
  * loops touch, e.g. DiT pos_embed: DiT/forget.py:58-62). */
 SFR_API int sfr_ema_update(const float* p, float* ema, int64_t n, int ema_mode, double ema_a,
                    sfr_stream_t stream);
+
+/* ===========================================================================
+ * Consumers next to the hot path
+ *
+ * EWC / Selective-Amnesia penalty — DDPM/runners/diffusion.py:424-433 (sa_forget):
+ *   per step, per tensor:  _loss = fisher * (param - params_mle)**2 ; loss += lmbda * _loss.sum()
+ * One pass adds autograd's gradient of that term, (lmbda*F) * (2*(p - p_star)), into g and
+ * accumulates the penalty value lmbda * sum(F * (p - p_star)^2) into *penalty (device double, may be NULL).
+ *
+ * Proximal-gradient shrink — SD/train-scripts/proximal_gradient.py:151-183:
+ *   threshold = k-th smallest |theta - theta0|: run the K2b select with key mode SFR_KEY_ABSDIFF and
+ *   k' = n - k + 1 (k-th smallest = k'-th largest), read it with sfr_select_threshold_value, then
+ *   sfr_soft_threshold: d = p - p0 ; d > thr: d -= thr ; d < -thr: d += thr ; else 0 ; p = d + p0.
+ * ======================================================================== */
+SFR_API int sfr_ewc_penalty(const float* p, const float* p_star, const float* fisher, float* g,
+                    int64_t n, float lambda, double* penalty, sfr_stream_t stream);
+SFR_API int sfr_select_threshold_value(const sfr_select_state* state_dev, float* out_dev,
+                               sfr_stream_t stream);
+SFR_API int sfr_soft_threshold(float* p, const float* p0, int64_t n, const float* threshold_dev,
+                       sfr_stream_t stream);
 
 /* ===========================================================================
  * Flat-gradient capture: gather `count` gradient tensors into the flat vector

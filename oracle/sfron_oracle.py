@@ -303,3 +303,43 @@ def flat_masked_clip_(g: Tensor, mask: Optional[Tensor], max_norm: Optional[floa
         p = torch.nn.Parameter(g.detach())  # shares storage
         p.grad = g
         torch.nn.utils.clip_grad_norm_([p], max_norm)
+
+
+# --------------------------------------------------------------------------- §8f n2 / n3 consumers
+def ewc_penalty_grads(params: Dict[str, Tensor], params_mle: Dict[str, Tensor], fisher: Dict[str, Tensor],
+                      lmbda: float):
+    """Selective-Amnesia / EWC term of DDPM sa_forget, through autograd exactly as written:
+    `_loss = fisher[name] * (param - params_mle[name]) ** 2 ; loss += lmbda * _loss.sum()`
+    (DDPM/runners/diffusion.py:424-433).  Returns ({name: d loss / d param}, ewc_loss)."""
+    leaves = {n: p.detach().clone().requires_grad_(True) for n, p in params.items()}
+    loss = 0.0
+    for name, param in leaves.items():
+        _loss = fisher[name] * (param - params_mle[name]) ** 2
+        loss = loss + lmbda * _loss.sum()
+    loss.backward()
+    return {n: p.grad for n, p in leaves.items()}, loss.detach()
+
+
+def proximal_step_(params: Sequence[Tensor], init_params: Sequence[Tensor], ratio: int) -> Tensor:
+    """The shrink of SD/train-scripts/proximal_gradient.py:151-183 on CPU tensors (in place):
+    threshold = -topk(-|theta - theta0|, ratio)[0][-1], then soft-threshold theta - theta0."""
+    n_params = sum(p.numel() for p in params)
+    flat = torch.zeros(n_params)
+    flat_init = torch.cat([p.reshape(-1) for p in init_params])
+    cnt = 0
+    for p in params:
+        flat[cnt:cnt + p.numel()] = p.reshape(-1)
+        cnt += p.numel()
+    flat -= flat_init
+    flat.abs_().neg_()
+    threshold = -torch.topk(flat, ratio)[0][-1]
+    for p, init_param in zip(params, init_params):
+        p -= init_param
+        larger = p > threshold
+        smaller = p < -threshold
+        between = ~(larger | smaller)
+        p[larger] -= threshold
+        p[smaller] += threshold
+        p[between] = 0
+        p += init_param
+    return threshold

@@ -456,3 +456,37 @@ def test_errors_are_loud(sfr, dev):
     capi.fisher_accum(torch.zeros(0, device=dev), torch.zeros(0, device=dev), 1.0)
     sm, major, _ = capi.device_info()
     assert major == 10 and sm > 0
+
+
+# =============================================================================== §8f n2 / n3 consumers
+@pytest.mark.parametrize("n", [5, 4099, 300_001])
+def test_ewc_penalty_matches_autograd(sfr, dev, n):
+    g = gen(n + 3)
+    p, ps = torch.randn(n, generator=g) * 0.02, torch.randn(n, generator=g) * 0.02
+    fisher = torch.randn(n, generator=g).pow(2) * 1e-3
+    g0 = torch.randn(n, generator=g) * 0.01
+    lmbda = 50.0
+    grads, ewc = O.ewc_penalty_grads({"w": p}, {"w": ps}, {"w": fisher}, lmbda)
+    hp = sfr.HotPath(n, dev, sfr.OptConfig())
+    gd = g0.to(dev)
+    pen = hp.ewc_penalty(p.to(dev), ps.to(dev), fisher.to(dev), gd, lmbda)
+    assert bits_equal(gd.cpu(), g0 + grads["w"])                 # model grad + EWC grad, as autograd sums them
+    assert abs(pen.item() - ewc.item()) <= 1e-6 * abs(ewc.item())
+
+
+@pytest.mark.parametrize("n", [7, 10_003, 1_000_003])
+@pytest.mark.parametrize("frac", [0.001, 0.3, 0.9])
+def test_proximal_shrink_bit_exact(sfr, dev, n, frac):
+    g = gen(n + 17)
+    p0 = torch.randn(n, generator=g) * 0.02
+    p = p0 + torch.randn(n, generator=g) * 1e-3
+    same = torch.rand(n, generator=g) < 0.1
+    p[same] = p0[same]                                            # exact zeros of theta - theta0
+    k = max(1, int(n * frac))
+    ref = p.clone()
+    thr = O.proximal_step_([ref], [p0.clone()], k)
+    hp = sfr.HotPath(n, dev, sfr.OptConfig())
+    pd = p.to(dev)
+    got_thr = hp.proximal_shrink(pd, p0.to(dev), k)
+    assert got_thr.item() == thr.item()
+    assert bits_equal(pd.cpu(), ref)

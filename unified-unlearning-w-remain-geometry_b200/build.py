@@ -20,7 +20,7 @@ LIB_NAME = "libsfron_b200.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
 STAMP_PATH = os.path.join(HERE, ".libsfron_b200.stamp")
 
-SOURCES = ["api.cu", "fisher.cu", "mask.cu", "select.cu", "update.cu"]
+SOURCES = ["api.cu", "fisher.cu", "mask.cu", "select.cu", "update.cu", "extras.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

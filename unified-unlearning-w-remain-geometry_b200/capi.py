@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, "libsfron_b200.so")
 ABI_VERSION = 1
 OK, ERR_NULL, ERR_ALIGN, ERR_ARG, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 F32, BF16 = 0, 1
-KEY_ABS, KEY_RATIO = 0, 1
+KEY_ABS, KEY_RATIO, KEY_ABSDIFF = 0, 1, 2
 SELECT_BINS0, SELECT_BINS1 = 32768, 65536
 MAX_THRESHOLDS = 8
 OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2
@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = (
     "sfr_ratio_mask", "sfr_ratio_mask_multi", "sfr_select_init", "sfr_select_hist",
     "sfr_select_scan", "sfr_select_scratch_elems", "sfr_select_apply", "sfr_masked_sumsq",
     "sfr_fused_update", "sfr_ema_update", "sfr_gather_segments",
+    "sfr_ewc_penalty", "sfr_select_threshold_value", "sfr_soft_threshold",
 )
 
 
@@ -112,6 +113,12 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.sfr_ema_update.argtypes = [vp, vp, i64, C.c_int, f64, vp]
     lib.sfr_gather_segments.restype = C.c_int
     lib.sfr_gather_segments.argtypes = [vp, vp, vp, vp, i32, C.c_int, i64, vp]
+    lib.sfr_ewc_penalty.restype = C.c_int
+    lib.sfr_ewc_penalty.argtypes = [vp, vp, vp, vp, i64, f32, vp, vp]
+    lib.sfr_select_threshold_value.restype = C.c_int
+    lib.sfr_select_threshold_value.argtypes = [vp, vp, vp]
+    lib.sfr_soft_threshold.restype = C.c_int
+    lib.sfr_soft_threshold.argtypes = [vp, vp, i64, vp, vp]
     if lib.sfr_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libsfron_b200 ABI {lib.sfr_abi_version()} != binding {ABI_VERSION}")
     if path == LIB_PATH:
@@ -283,3 +290,28 @@ def gather_segments(flat: torch.Tensor, srcs: torch.Tensor, offsets: torch.Tenso
     _check(load().sfr_gather_segments(_ptr(flat, torch.float32, "flat"), _ptr(srcs, torch.int64, "srcs"),
                                       _ptr(offsets, torch.int64, "offsets"), _ptr(sizes, torch.int64, "sizes"),
                                       srcs.numel(), src_dtype, int(total), _stream()), "sfr_gather_segments")
+
+
+# ---- consumers next to the path -------------------------------------------
+def ewc_penalty(p: torch.Tensor, p_star: torch.Tensor, fisher: torch.Tensor, g: torch.Tensor, lmbda: float,
+                penalty: Optional[torch.Tensor] = None) -> None:
+    """g += (lmbda*F) * (2*(p - p_star)); penalty (device float64) += lmbda * sum(F * (p - p_star)**2)."""
+    n = p.numel()
+    if not (p_star.numel() == fisher.numel() == g.numel() == n):
+        raise SfrError(ERR_ARG, "ewc_penalty", "size mismatch")
+    _check(load().sfr_ewc_penalty(_ptr(p, torch.float32, "p"), _ptr(p_star, torch.float32, "p_star"),
+                                  _ptr(fisher, torch.float32, "fisher"), _ptr(g, torch.float32, "g"), n,
+                                  float(lmbda), _ptr(penalty, torch.float64, "penalty"), _stream()),
+           "sfr_ewc_penalty")
+
+
+def select_threshold_value(state: torch.Tensor, out: torch.Tensor) -> None:
+    _check(load().sfr_select_threshold_value(_ptr(state, torch.int64, "state"), _ptr(out, torch.float32, "out"),
+                                             _stream()), "sfr_select_threshold_value")
+
+
+def soft_threshold(p: torch.Tensor, p0: torch.Tensor, threshold: torch.Tensor) -> None:
+    if p.numel() != p0.numel():
+        raise SfrError(ERR_ARG, "soft_threshold", "size mismatch")
+    _check(load().sfr_soft_threshold(_ptr(p, torch.float32, "p"), _ptr(p0, torch.float32, "p0"), p.numel(),
+                                     _ptr(threshold, torch.float32, "threshold"), _stream()), "sfr_soft_threshold")

@@ -26,8 +26,10 @@ template <int MODE>
 __device__ __forceinline__ uint32_t key_from(float a, float b, float eps) {
   if constexpr (MODE == SFR_KEY_ABS) {
     return select_key(a);
-  } else {
+  } else if constexpr (MODE == SFR_KEY_RATIO) {
     return select_key(__fdiv_rn(__fadd_rn(a, eps), __fadd_rn(b, eps)));
+  } else {  // SFR_KEY_ABSDIFF: |a - b|  (proximal_gradient.py:158-159: params -= init ; abs_())
+    return select_key(__fsub_rn(a, b));
   }
 }
 
@@ -82,7 +84,7 @@ select_hist0_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
       const int64_t v = base + (int64_t)u * kHistThreads;
       const bool in = v < nvec;
       x[u] = in ? ld_stream(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if constexpr (MODE == SFR_KEY_RATIO)
+      if constexpr (MODE != SFR_KEY_ABS)
         y[u] = in ? ld_stream(b4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
       else
         y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -100,7 +102,7 @@ select_hist0_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
   const int64_t tail0 = nvec << 2;
   if (blockIdx.x == 0 && threadIdx.x < (n - tail0)) {
     const int64_t i = tail0 + threadIdx.x;
-    rc.push(hist, key_from<MODE>(a[i], MODE == SFR_KEY_RATIO ? b[i] : 0.f, eps) >> 16);
+    rc.push(hist, key_from<MODE>(a[i], MODE != SFR_KEY_ABS ? b[i] : 0.f, eps) >> 16);
   }
   rc.flush(hist);
   __syncthreads();
@@ -185,7 +187,7 @@ select_hist1_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
       const int64_t v = base + (int64_t)u * kFiltThreads;
       const bool in = v < nvec;
       x[u] = in ? ld_stream(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if constexpr (MODE == SFR_KEY_RATIO)
+      if constexpr (MODE != SFR_KEY_ABS)
         y[u] = in ? ld_stream(b4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
       else
         y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -207,7 +209,7 @@ select_hist1_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
   const int64_t tail0 = nvec << 2;
   if (blockIdx.x == 0 && threadIdx.x < (n - tail0)) {
     const int64_t i = tail0 + threadIdx.x;
-    const uint32_t k = key_from<MODE>(a[i], MODE == SFR_KEY_RATIO ? b[i] : 0.f, eps);
+    const uint32_t k = key_from<MODE>(a[i], MODE != SFR_KEY_ABS ? b[i] : 0.f, eps);
     if ((k >> 16) == prefix) { rc.push(bins, k & 0xffffu); cs.push(i, k); }
   }
   rc.flush(bins);
@@ -357,7 +359,7 @@ __device__ __forceinline__ void load_chunk_keys(const float* __restrict__ a, con
     for (int sl = 0; sl < kChunkVecs; ++sl) {
       const int64_t e0 = base + ((int64_t)sl * kApplyThreads + threadIdx.x) * 4;
       x[sl] = ld_stream(reinterpret_cast<const float4*>(a + e0));
-      if constexpr (MODE == SFR_KEY_RATIO) y[sl] = ld_stream(reinterpret_cast<const float4*>(b + e0));
+      if constexpr (MODE != SFR_KEY_ABS) y[sl] = ld_stream(reinterpret_cast<const float4*>(b + e0));
       else y[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
@@ -375,7 +377,7 @@ __device__ __forceinline__ void load_chunk_keys(const float* __restrict__ a, con
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const bool ok = e0 + q < n;
-        key[sl][q] = ok ? key_from<MODE>(a[e0 + q], MODE == SFR_KEY_RATIO ? b[e0 + q] : 0.f, eps) : 0u;
+        key[sl][q] = ok ? key_from<MODE>(a[e0 + q], MODE != SFR_KEY_ABS ? b[e0 + q] : 0.f, eps) : 0u;
         valid_bits |= (ok ? 1u : 0u) << (sl * 4 + q);
       }
     }
@@ -383,7 +385,7 @@ __device__ __forceinline__ void load_chunk_keys(const float* __restrict__ a, con
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kApplyThreads, MODE == SFR_KEY_RATIO ? 2 : 4)
+__global__ void __launch_bounds__(kApplyThreads, MODE != SFR_KEY_ABS ? 2 : 4)
 select_tie_count_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps,
                         int64_t n, const sfr_select_state* __restrict__ state,
                         unsigned long long* __restrict__ scratch) {
@@ -508,7 +510,7 @@ select_apply_stream_kernel(const float* __restrict__ a, const float* __restrict_
       const int64_t v = base + (int64_t)u * kApplyThreads;
       const bool in = v < nvec;
       x[u] = in ? ld_stream(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if constexpr (MODE == SFR_KEY_RATIO)
+      if constexpr (MODE != SFR_KEY_ABS)
         y[u] = in ? ld_stream(b4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
       else
         y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -527,13 +529,13 @@ select_apply_stream_kernel(const float* __restrict__ a, const float* __restrict_
   const int64_t tail0 = nvec << 2;
   if (blockIdx.x == 0 && threadIdx.x < (n - tail0)) {
     const int64_t i = tail0 + threadIdx.x;
-    mask[i] = (uint8_t)(!none && key_from<MODE>(a[i], MODE == SFR_KEY_RATIO ? b[i] : 0.f, eps) >= thr);
+    mask[i] = (uint8_t)(!none && key_from<MODE>(a[i], MODE != SFR_KEY_ABS ? b[i] : 0.f, eps) >= thr);
   }
 }
 
 // More threshold-equal keys than the budget: lowest flat index first.
 template <int MODE>
-__global__ void __launch_bounds__(kApplyThreads, MODE == SFR_KEY_RATIO ? 2 : 4)
+__global__ void __launch_bounds__(kApplyThreads, MODE != SFR_KEY_ABS ? 2 : 4)
 select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps,
                     int64_t n, const sfr_select_state* __restrict__ state,
                     const unsigned long long* __restrict__ scratch, uint8_t* __restrict__ mask) {
@@ -555,7 +557,7 @@ select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
       for (int sl = 0; sl < kChunkVecs; ++sl) {
         const int64_t e0 = base + ((int64_t)sl * kApplyThreads + threadIdx.x) * 4;
         x[sl] = ld_stream(reinterpret_cast<const float4*>(a + e0));
-        if constexpr (MODE == SFR_KEY_RATIO) y[sl] = ld_stream(reinterpret_cast<const float4*>(b + e0));
+        if constexpr (MODE != SFR_KEY_ABS) y[sl] = ld_stream(reinterpret_cast<const float4*>(b + e0));
         else y[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
@@ -649,12 +651,12 @@ extern "C" int sfr_select_hist(const float* a, const float* b, int key_mode, flo
                                sfr_stream_t stream) {
   using namespace sfr;
   if (n < 0 || (pass != 0 && pass != 1)) return SFR_ERR_ARG;
-  if (key_mode != SFR_KEY_ABS && key_mode != SFR_KEY_RATIO) return SFR_ERR_ARG;
+  if (key_mode < SFR_KEY_ABS || key_mode > SFR_KEY_ABSDIFF) return SFR_ERR_ARG;
   SFR_REQUIRE_PTR(bins);
   SFR_REQUIRE_PTR(state);
   if (n == 0) return SFR_OK;
   SFR_REQUIRE_PTR(a);
-  if (key_mode == SFR_KEY_RATIO) SFR_REQUIRE_PTR(b);
+  if (key_mode != SFR_KEY_ABS) SFR_REQUIRE_PTR(b);
   SFR_REQUIRE_ALIGNED(a);
   SFR_REQUIRE_ALIGNED(b);
   if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
@@ -666,12 +668,14 @@ extern "C" int sfr_select_hist(const float* a, const float* b, int key_mode, flo
     if (!attr_done) {
       cudaFuncSetAttribute(select_hist0_kernel<SFR_KEY_ABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       cudaFuncSetAttribute(select_hist0_kernel<SFR_KEY_RATIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(select_hist0_kernel<SFR_KEY_ABSDIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       attr_done = true;
     }
     const int64_t tile = (int64_t)kHistThreads * kHistUnroll;
     const int grid = persistent_grid((nvec + tile - 1) / tile, 1);
     if (key_mode == SFR_KEY_ABS) select_hist0_kernel<SFR_KEY_ABS><<<grid, kHistThreads, smem, s>>>(a, b, eps, n, bins);
-    else select_hist0_kernel<SFR_KEY_RATIO><<<grid, kHistThreads, smem, s>>>(a, b, eps, n, bins);
+    else if (key_mode == SFR_KEY_RATIO) select_hist0_kernel<SFR_KEY_RATIO><<<grid, kHistThreads, smem, s>>>(a, b, eps, n, bins);
+    else select_hist0_kernel<SFR_KEY_ABSDIFF><<<grid, kHistThreads, smem, s>>>(a, b, eps, n, bins);
   } else {
     const int64_t tile = (int64_t)kFiltThreads * kFiltUnroll;
     SFR_REQUIRE_PTR(scratch);
@@ -680,7 +684,8 @@ extern "C" int sfr_select_hist(const float* a, const float* b, int key_mode, flo
     // zero the per-chunk tie counters and the candidate header (the regions need no clearing)
     cudaMemsetAsync(scratch, 0, (size_t)(2 * scratch_nchunks(n) + kCandHeader) * sizeof(unsigned long long), s);
     if (key_mode == SFR_KEY_ABS) select_hist1_kernel<SFR_KEY_ABS><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins, scratch);
-    else select_hist1_kernel<SFR_KEY_RATIO><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins, scratch);
+    else if (key_mode == SFR_KEY_RATIO) select_hist1_kernel<SFR_KEY_RATIO><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins, scratch);
+    else select_hist1_kernel<SFR_KEY_ABSDIFF><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins, scratch);
   }
   SFR_LAUNCH_STATUS();
 }
@@ -709,11 +714,11 @@ extern "C" int sfr_select_apply(const float* a, const float* b, int key_mode, fl
                                 sfr_stream_t stream) {
   using namespace sfr;
   if (n < 0) return SFR_ERR_ARG;
-  if (key_mode != SFR_KEY_ABS && key_mode != SFR_KEY_RATIO) return SFR_ERR_ARG;
+  if (key_mode < SFR_KEY_ABS || key_mode > SFR_KEY_ABSDIFF) return SFR_ERR_ARG;
   SFR_REQUIRE_PTR(state);
   if (n == 0) return SFR_OK;
   SFR_REQUIRE_PTR(a);
-  if (key_mode == SFR_KEY_RATIO) SFR_REQUIRE_PTR(b);
+  if (key_mode != SFR_KEY_ABS) SFR_REQUIRE_PTR(b);
   SFR_REQUIRE_PTR(scratch);
   SFR_REQUIRE_PTR(mask);
   SFR_REQUIRE_ALIGNED(a);
@@ -728,16 +733,16 @@ extern "C" int sfr_select_apply(const float* a, const float* b, int key_mode, fl
   // the per-chunk counters are accumulated into: clear them here so that apply is idempotent
   cudaMemsetAsync(scratch, 0, (size_t)nchunks * sizeof(unsigned long long), s);
   select_tie_count_candidates_kernel<<<persistent_grid(kMaxRegions, 8), 256, 0, s>>>(n, state, scratch);
-  if (key_mode == SFR_KEY_ABS) {
-    select_tie_count_kernel<SFR_KEY_ABS><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch);
-    select_tie_scan_kernel<<<1, 1024, 0, s>>>(nchunks, state, tie_base, scratch);
-    select_apply_kernel<SFR_KEY_ABS><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch, mask);
-    select_apply_stream_kernel<SFR_KEY_ABS><<<sgrid, kApplyThreads, 0, s>>>(a, b, eps, n, state, mask);
-  } else {
-    select_tie_count_kernel<SFR_KEY_RATIO><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch);
-    select_tie_scan_kernel<<<1, 1024, 0, s>>>(nchunks, state, tie_base, scratch);
-    select_apply_kernel<SFR_KEY_RATIO><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch, mask);
-    select_apply_stream_kernel<SFR_KEY_RATIO><<<sgrid, kApplyThreads, 0, s>>>(a, b, eps, n, state, mask);
-  }
+#define SFR_APPLY(M)                                                                                     \
+  do {                                                                                                   \
+    select_tie_count_kernel<M><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch);             \
+    select_tie_scan_kernel<<<1, 1024, 0, s>>>(nchunks, state, tie_base, scratch);                        \
+    select_apply_kernel<M><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch, mask);           \
+    select_apply_stream_kernel<M><<<sgrid, kApplyThreads, 0, s>>>(a, b, eps, n, state, mask);            \
+  } while (0)
+  if (key_mode == SFR_KEY_ABS) SFR_APPLY(SFR_KEY_ABS);
+  else if (key_mode == SFR_KEY_RATIO) SFR_APPLY(SFR_KEY_RATIO);
+  else SFR_APPLY(SFR_KEY_ABSDIFF);
+#undef SFR_APPLY
   SFR_LAUNCH_STATUS();
 }

@@ -111,6 +111,9 @@ class ShardedHotPath(HotPath):
     def reduce_scalar_(self, t: torch.Tensor) -> None:
         self.shards.all_reduce_(t)
 
+    def total_elements(self) -> int:
+        return self.shards.n_total
+
     def reduce_bins_(self, bins: torch.Tensor, count: int) -> None:
         self.shards.all_reduce_(bins[:count])
 

@@ -177,6 +177,39 @@ class HotPath:
         capi.select_apply(values, other, mode, state, tie_base, scratch, mask, eps)
         return mask
 
+    def kth_smallest_absdiff(self, a: torch.Tensor, b: torch.Tensor, k: int) -> torch.Tensor:
+        """The k-th smallest |a - b| as a device fp32 scalar (k is global, 1-based): the threshold of
+        SD/train-scripts/proximal_gradient.py:161 (`-topk(-|theta - theta0|, k)[0][-1]`)."""
+        state, bins, scratch = self._select_buffers()
+        n_total = self.total_elements()
+        capi.select_init(state, bins, n_total - k + 1)          # k-th smallest == (n-k+1)-th largest
+        capi.select_hist(a, b, capi.KEY_ABSDIFF, 0, state, bins, None)
+        self.reduce_bins_(bins, capi.SELECT_BINS0)
+        capi.select_scan(0, state, bins)
+        capi.select_hist(a, b, capi.KEY_ABSDIFF, 1, state, bins, scratch)
+        self.reduce_bins_(bins, capi.SELECT_BINS1)
+        capi.select_scan(1, state, bins)
+        out = torch.empty(1, dtype=torch.float32, device=self.device)
+        capi.select_threshold_value(state, out)
+        return out
+
+    def proximal_shrink(self, p: torch.Tensor, p0: torch.Tensor, k: int) -> torch.Tensor:
+        """proximal_gradient.py:151-183: soft-threshold theta - theta0 at its k-th smallest magnitude."""
+        thr = self.kth_smallest_absdiff(p, p0, k)
+        capi.soft_threshold(p, p0, thr)
+        return thr
+
+    def ewc_penalty(self, p: torch.Tensor, p_star: torch.Tensor, fisher: torch.Tensor, g: torch.Tensor,
+                    lmbda: float) -> torch.Tensor:
+        """runners/diffusion.py:424-433: adds the EWC gradient into g; returns the penalty (device double)."""
+        pen = torch.zeros(1, dtype=torch.float64, device=self.device)
+        capi.ewc_penalty(p, p_star, fisher, g, lmbda, pen)
+        self.reduce_scalar_(pen)
+        return pen
+
+    def total_elements(self) -> int:
+        return self.n
+
     def select_state(self) -> capi.SelectState:
         return capi.read_select_state(self._select_buffers()[0])
 

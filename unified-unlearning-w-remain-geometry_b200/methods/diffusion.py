@@ -148,6 +148,25 @@ class DiffusionUnlearner:
             if log_every and (step + 1) % log_every == 0:
                 print(f"step:{step:04d} forget a:{alpha:.8f}")
 
+    # ---- consumers next to the path -------------------------------------------
+    def snapshot_params(self, role: str = "params_mle") -> torch.Tensor:
+        """`params_mle_dict[name] = param.data.clone()` (runners/diffusion.py:391-393) /
+        `gpu1_init_params` (proximal_gradient.py): a flat copy of the current weights."""
+        buf = self.mhp.hp.buffer(role)
+        buf.copy_(self.mhp.flat.p)
+        return buf
+
+    def add_ewc_penalty(self, lmbda: float, fisher_role: str = "fim") -> torch.Tensor:
+        """Selective-Amnesia term of sa_forget: call after `loss.backward()`; adds the gradient of
+        `lmbda * sum(F * (p - p_mle)**2)` into the flat gradient and returns the penalty value."""
+        hp = self.mhp.hp
+        return hp.ewc_penalty(self.mhp.flat.p, hp.buffer("params_mle"), hp.buffer(fisher_role), self.mhp.grads(), lmbda)
+
+    def proximal_shrink(self, k: int, init_role: str = "params_init") -> torch.Tensor:
+        """proximal_gradient.py:151-183 after `optimizer.step()`: soft-threshold theta - theta0 at its
+        k-th smallest magnitude; returns the threshold (device scalar)."""
+        return self.mhp.hp.proximal_shrink(self.mhp.flat.p, self.mhp.hp.buffer(init_role), k)
+
     # ---- checkpoints -------------------------------------------------------------------------------
     def checkpoint(self, step: int = 0, args=None):
         """DDPM: [model_sd, opt_sd, step, ema_shadow]; DiT: {model, ema, opt, args}; SD: state_dict."""
