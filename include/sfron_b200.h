@@ -234,9 +234,15 @@ typedef struct sfr_update_args {
   double clip_max_norm;/* used when clip_sumsq != NULL                    */
 } sfr_update_args;
 
+/* step_counter_dev / consts_scratch_dev: NULL for plain launches (args->step is used).  For launches
+ * that will be REPLAYED (CUDA graphs) pass a device int64 counter and >= 128 bytes of 16-byte-aligned
+ * device scratch: a one-thread kernel increments the counter and forms the step-dependent constants
+ * (bias corrections, SGD first-step flag) on the device, so every replay advances the optimizer step. */
+#define SFR_UPDATE_CONSTS_BYTES 128
 SFR_API int sfr_fused_update(float* p, void* g, float* m, float* v, const uint8_t* mask,
                      float* ema, void* p_bf16, int64_t n,
                      const sfr_update_args* args, const double* clip_sumsq,
+                     long long* step_counter_dev, void* consts_scratch_dev,
                      sfr_stream_t stream);
 
 /* EMA / slow-weight pass alone (frozen parameters that only the reference's EMA

@@ -196,3 +196,39 @@ def test_ddpm_family_loop_fisher_and_topk(dev, tmp_path):
     import pickle
     with open(tmp_path / "fisher_dict.pkl", "rb") as f:
         assert list(pickle.load(f).keys()) == ["module." + n for n in sx["names"]]
+
+
+def test_bf16_model_mixed_precision_flat_params(dev):
+    """BASELINE config 3 (bf16): module weights / grads are bf16 views, the kernels keep an fp32 master."""
+    import sfron_b200 as sfr
+    from sfron_b200.methods.common import ModelHotPath
+    from oracle import sfron_oracle as O
+    torch.manual_seed(0)
+    model = TinyNet().to(dev).to(torch.bfloat16)
+    theta0 = torch.cat([p.detach().float().reshape(-1) for p in model.parameters()]).cpu()
+    mhp = ModelHotPath(model, sfr.OptConfig(kind="adamw", lr=1e-3), ema_mode="dit", ema_a=0.999)
+    fp = mhp.flat
+    assert fp.p.dtype == torch.float32 and fp.g.dtype == torch.bfloat16 and fp.p_work.dtype == torch.bfloat16
+    assert next(model.parameters()).data_ptr() == fp.p_work.data_ptr()
+    n = fp.n
+    ref = O.FlatReferenceLoop({"w": (n,)}, {"w": theta0}, "adamw", dict(lr=1e-3), ema_mode="dit", ema_a=0.999)
+    mhp.hp.mask.fill_(1)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(3):
+        grad = (torch.randn(n, generator=g) * 0.1).bfloat16()
+        inject(model, grad.float()).backward()           # bf16 params -> bf16 grads land in the flat g
+        assert torch.equal(fp.g.cpu(), grad)
+        mhp.remain_step(max_norm=1.0)
+        ref.remain_step({"w": grad.float()}, max_norm=1.0)
+        assert int(fp.g.count_nonzero()) == 0             # fused zero_grad
+    assert close(fp.p, ref.flat("p"))                     # fp32 master follows the fp32 oracle
+    assert torch.equal(fp.p_work, fp.p.bfloat16())        # working copy = rounded master
+    assert torch.equal(next(model.parameters()).reshape(-1), fp.p_work[:216])
+
+
+def test_padded_flat_params_views_and_length(dev):
+    import sfron_b200 as sfr
+    model = TinyNet().to(dev)
+    fp = sfr.FlatParams(model, dev, pad_multiple=128)
+    assert fp.n == 554 and fp.n_padded == 640 and fp.p.numel() == 554
+    assert fp.p.data_ptr() == fp.p_padded.data_ptr() and int(fp.p_padded[554:].abs().sum()) == 0

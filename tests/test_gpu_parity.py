@@ -490,3 +490,48 @@ def test_proximal_shrink_bit_exact(sfr, dev, n, frac):
     got_thr = hp.proximal_shrink(pd, p0.to(dev), k)
     assert got_thr.item() == thr.item()
     assert bits_equal(pd.cpu(), ref)
+
+
+# =============================================================================== CUDA-graph replay
+@pytest.mark.parametrize("opt,kw,ema_mode,ema_a", [CASES[0], CASES[3], CASES[5]])
+def test_k3_cuda_graph_replay_advances_device_step(sfr, dev, opt, kw, ema_mode, ema_a):
+    """forget_step + remain_step captured once and replayed: the optimizer step (Adam bias corrections,
+    SGD first-step buffer init) must advance on the device at every replay."""
+    n = 50_003
+    g = gen(77)
+    theta0 = torch.randn(n, generator=g) * 0.02
+    mask = torch.rand(n, generator=g) < 0.35
+    ref = flat_loop(n, theta0, opt, kw, ema_mode, ema_a)
+    hp, p = engine_for(sfr, dev, n, theta0, opt, kw, ema_mode, ema_a)
+    hp.set_buffer("mask", mask.to(torch.uint8).to(dev))
+    hp.enable_graph_replay()
+    gf_s, gr_s = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+
+    def body():
+        hp.forget_step(p, gf_s, max_norm=1.0)
+        hp.remain_step(p, gr_s, ema=True)
+
+    steps = [(torch.randn(n, generator=g) * (3.0 if i % 2 else 0.01), torch.randn(n, generator=g) * 0.1)
+             for i in range(6)]
+    # eager step 0 on a side stream (warm-up, also exercises the device counter outside a graph)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        gf_s.copy_(steps[0][0]); gr_s.copy_(steps[0][1])
+        body()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    gf_s.copy_(steps[1][0]); gr_s.copy_(steps[1][1])
+    with torch.cuda.graph(graph):
+        body()
+    graph.replay()                                     # capture does not execute: first real run of step 1
+    for gf, gr in steps[2:]:
+        gf_s.copy_(gf); gr_s.copy_(gr)
+        graph.replay()
+    for gf, gr in steps:
+        ref.forget_step({"w": gf}, mask={"w": mask}, max_norm=1.0)
+        ref.remain_step({"w": gr}, ema=True)
+    assert int(hp.step_dev) == 2 * len(steps)
+    assert close(p, ref.flat("p"))
+    if ema_mode != "none":
+        assert close(hp.slow, ref.flat("slow"))

@@ -32,10 +32,10 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 from dit_xl2 import DiTXL2Harness, synthetic_loss  # noqa: E402
 
 
-def make_batch(bs, dev, gen, forget_class=207):
-    x = torch.randn(bs, 4, 32, 32, device=dev, generator=gen)
+def make_batch(bs, dev, gen, forget_class=207, dtype=torch.float32):
+    x = torch.randn(bs, 4, 32, 32, device=dev, generator=gen).to(dtype)
     t = torch.randint(0, 1000, (bs,), device=dev, generator=gen)
-    noise = torch.randn(bs, 4, 32, 32, device=dev, generator=gen)
+    noise = torch.randn(bs, 4, 32, 32, device=dev, generator=gen).to(dtype)
     y_f = torch.full((bs,), forget_class, device=dev)
     y_r = torch.randint(0, 1000, (bs,), device=dev, generator=gen)
     return x, t, noise, y_f, y_r
@@ -108,13 +108,15 @@ def run_ours(args, dev, ac, rank, world):
     import sfron_b200 as sfr
     torch.manual_seed(0)
     model = DiTXL2Harness().to(dev)
+    if args.dtype == "bf16":
+        model = model.to(torch.bfloat16)      # bf16 working weights + grads; fp32 master / state in the kernels
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     opt = sfr.OptConfig(kind="adamw", lr=1e-4, weight_decay=0.0)
-    flat = sfr.FlatParams(model, dev)
+    flat = sfr.FlatParams(model, dev, pad_multiple=16 * world)
     if world > 1:
         import torch.distributed as dist
         from sfron_b200.dist import ShardGroup, ShardedHotPath
-        sg = ShardGroup(flat.n)
+        sg = ShardGroup(flat.n, padded_len=flat.n_padded)
         hp = ShardedHotPath(sg, dev, opt, ema_mode="dit", ema_a=0.9999)
         lo, hi = sg.lo, sg.hi
     else:
@@ -122,6 +124,8 @@ def run_ours(args, dev, ac, rank, world):
         hp = sfr.HotPath(flat.n, dev, opt, ema_mode="dit", ema_a=0.9999)
         lo, hi = 0, flat.n
     p_loc = flat.p[lo:hi]
+    w_loc = None if flat.p_work is None else flat.p_work[lo:hi]
+    weights_full = flat.p_padded if flat.p_work is None else flat.p_work_padded   # what the model reads
     hp.init_slow(p_loc)
     frozen_slow = flat.frozen.clone()
     hp.mask.copy_((torch.rand(hi - lo, device=dev, generator=gen) < 0.5).to(torch.uint8))
@@ -135,30 +139,74 @@ def run_ours(args, dev, ac, rank, world):
 
     def grads():
         if sg is not None:
-            return sg.reduce_gradients_(flat.g, average=True)
+            if args.dp_exchange == "allreduce":
+                return sg.reduce_gradients_(flat.g_padded, average=True)[:sg.n_local]
+            return sg.reduce_scatter_gradients_(flat.g_padded, average=True)
         return flat.g
 
+    dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    ac = ac.to(dt)
+
     def forget_iter(i):
-        x, t, noise, y_f, y_r = make_batch(args.batch_size, dev, gen)
+        x, t, noise, y_f, y_r = make_batch(args.batch_size, dev, gen, dtype=dt)
         (args.forget_alpha * -synthetic_loss(model, x, t, y_f, noise, ac)).backward()
         # single GPU: the update kernel zeroes g on its way out (fused optimizer.zero_grad());
         # sharded: each rank only rewrites its slice, so the full local gradient is memset
-        hp.forget_step(p_loc, grads(), max_norm=1.0, zero_grad=sg is None)
+        hp.forget_step(p_loc, grads(), max_norm=1.0, zero_grad=sg is None, p_bf16=w_loc)
         if sg is not None:
-            sg.all_gather_params_(flat.p)
+            sg.all_gather_params_(weights_full)
             flat.g.zero_()
         synthetic_loss(model, x, t, y_r, noise, ac).backward()
-        hp.remain_step(p_loc, grads(), ema=True, zero_grad=sg is None)
+        hp.remain_step(p_loc, grads(), ema=True, zero_grad=sg is None, p_bf16=w_loc)
         hp.ema_only(flat.frozen, frozen_slow)
         if sg is not None:
-            sg.all_gather_params_(flat.p)
+            sg.all_gather_params_(weights_full)
             flat.g.zero_()
 
     flat.g.zero_()
-    res["forget_s_per_it"] = timed(forget_iter, args.steps, args.warmup, sync)
+    if args.cuda_graph:
+        # Whole iteration (2 forward/backward passes in PyTorch + the hot-path kernels) captured ONCE and
+        # replayed: at batch 1 the forward/backward is launch-bound.  Inputs live in static buffers that
+        # are refilled before each replay; the optimizer step count lives on the device (replay-safe).
+        hp.enable_graph_replay()
+        static = list(make_batch(args.batch_size, dev, gen, dtype=dt))
+
+        def body():
+            x, t, noise, y_f, y_r = static
+            (args.forget_alpha * -synthetic_loss(model, x, t, y_f, noise, ac)).backward()
+            hp.forget_step(p_loc, grads(), max_norm=1.0, zero_grad=sg is None, p_bf16=w_loc)
+            if sg is not None:
+                sg.all_gather_params_(weights_full)
+                flat.g.zero_()
+            synthetic_loss(model, x, t, y_r, noise, ac).backward()
+            hp.remain_step(p_loc, grads(), ema=True, zero_grad=sg is None, p_bf16=w_loc)
+            hp.ema_only(flat.frozen, frozen_slow)
+            if sg is not None:
+                sg.all_gather_params_(weights_full)
+                flat.g.zero_()
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+
+        def graph_iter(i):
+            for dst, src in zip(static, make_batch(args.batch_size, dev, gen, dtype=dt)):
+                dst.copy_(src)
+            graph.replay()
+
+        res["forget_s_per_it"] = timed(graph_iter, args.steps, args.warmup, sync)
+        res["graph_steps_on_device"] = int(hp.step_dev)
+    else:
+        res["forget_s_per_it"] = timed(forget_iter, args.steps, args.warmup, sync)
 
     def fisher_iter(i):
-        x, t, noise, y_f, _ = make_batch(args.batch_size, dev, gen)
+        x, t, noise, y_f, _ = make_batch(args.batch_size, dev, gen, dtype=dt)
         synthetic_loss(model, x, t, y_f, noise, ac).backward()
         hp.fisher_accumulate("forget", grads(), 2000.0)
         flat.g.zero_()
@@ -175,6 +223,11 @@ def main():
     ap.add_argument("--batch-size", type=int, default=1, help="per GPU (DiT/forget.py default 1)")
     ap.add_argument("--forget-alpha", type=float, default=1e-3)
     ap.add_argument("--mask-on-device", action="store_true")
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="ours arm only: bf16 working weights / gradients with fp32 master + state (BASELINE config 3)")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="ours arm: capture the whole forget iteration (collectives included) in a CUDA graph and replay it")
+    ap.add_argument("--dp-exchange", default="reduce_scatter", choices=["reduce_scatter", "allreduce"])
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -198,7 +251,7 @@ def main():
         torch.cuda.empty_cache()
     if args.arm in ("both", "ours"):
         r = run_ours(args, dev, ac, rank, world)
-        out["ours"] = {"forget_steps_per_s": 1 / r["forget_s_per_it"], "fisher_steps_per_s": 1 / r["fisher_s_per_it"],
+        out["ours" + ("_bf16" if args.dtype == "bf16" else "") + ("_cudagraph" if args.cuda_graph else "")] = {"forget_steps_per_s": 1 / r["forget_s_per_it"], "fisher_steps_per_s": 1 / r["fisher_s_per_it"],
                        "global_batch": args.batch_size * world}
     if rank == 0:
         line = json.dumps(out)

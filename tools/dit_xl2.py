@@ -63,7 +63,8 @@ class _TimestepEmbedder(nn.Module):
         half = self.freq // 2
         freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
         args = t[:, None].float() * freqs[None]
-        return self.mlp(torch.cat([torch.cos(args), torch.sin(args)], dim=-1))
+        emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+        return self.mlp(emb.to(self.mlp[0].weight.dtype))
 
 
 class _LabelEmbedder(nn.Module):

@@ -108,7 +108,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.sfr_masked_sumsq.restype = C.c_int
     lib.sfr_masked_sumsq.argtypes = [vp, C.c_int, vp, i64, vp, vp]
     lib.sfr_fused_update.restype = C.c_int
-    lib.sfr_fused_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(UpdateArgs), vp, vp]
+    lib.sfr_fused_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(UpdateArgs), vp, vp, vp, vp]
     lib.sfr_ema_update.restype = C.c_int
     lib.sfr_ema_update.argtypes = [vp, vp, i64, C.c_int, f64, vp]
     lib.sfr_gather_segments.restype = C.c_int
@@ -265,7 +265,10 @@ def masked_sumsq(g: torch.Tensor, mask: Optional[torch.Tensor], out: torch.Tenso
 
 def fused_update(p: torch.Tensor, g: torch.Tensor, m: Optional[torch.Tensor], v: Optional[torch.Tensor],
                  mask: Optional[torch.Tensor], ema: Optional[torch.Tensor], args: UpdateArgs,
-                 clip_sumsq: Optional[torch.Tensor] = None, p_bf16: Optional[torch.Tensor] = None) -> None:
+                 clip_sumsq: Optional[torch.Tensor] = None, p_bf16: Optional[torch.Tensor] = None,
+                 step_counter: Optional[torch.Tensor] = None, consts_scratch: Optional[torch.Tensor] = None) -> None:
+    """step_counter (device int64[1]) + consts_scratch (device uint8[>=128]): replay-safe launch for CUDA
+    graphs — the optimizer step lives on the device and advances on every replay."""
     n = p.numel()
     for name, t in (("g", g), ("m", m), ("v", v), ("mask", mask), ("ema", ema), ("p_bf16", p_bf16)):
         if t is not None and t.numel() != n:
@@ -274,7 +277,9 @@ def fused_update(p: torch.Tensor, g: torch.Tensor, m: Optional[torch.Tensor], v:
     _check(load().sfr_fused_update(_ptr(p, torch.float32, "p"), _ptr(g, what="g"), _ptr(m, torch.float32, "m"),
                                    _ptr(v, torch.float32, "v"), _ptr(mask, _MASK_DTYPES, "mask"),
                                    _ptr(ema, torch.float32, "ema"), _ptr(p_bf16, torch.bfloat16, "p_bf16"), n,
-                                   C.byref(args), _ptr(clip_sumsq, torch.float64, "clip_sumsq"), _stream()),
+                                   C.byref(args), _ptr(clip_sumsq, torch.float64, "clip_sumsq"),
+                                   _ptr(step_counter, torch.int64, "step_counter"),
+                                   _ptr(consts_scratch, torch.uint8, "consts_scratch"), _stream()),
            "sfr_fused_update")
 
 

@@ -179,7 +179,11 @@ __global__ void __launch_bounds__(kThreads, kUpdCtasPerSm)
 fused_update_kernel(float* __restrict__ p, void* __restrict__ g, float* __restrict__ m,
                     float* __restrict__ v, const uint8_t* __restrict__ mask,
                     float* __restrict__ ema, void* __restrict__ p_bf16, int64_t n,
-                    UpdateConsts c, const double* __restrict__ clip_sumsq) {
+                    UpdateConsts c_arg, const UpdateConsts* __restrict__ c_dev,
+                    const double* __restrict__ clip_sumsq) {
+  // Replay-safe launches (CUDA graphs) read the step-dependent constants from device memory, where
+  // update_consts_kernel formed them from a device-side step counter; plain launches get them by value.
+  const UpdateConsts c = c_dev ? *c_dev : c_arg;
   constexpr bool kHasV = OPT != SFR_OPT_SGD;
   constexpr bool kHasEma = EMA != SFR_EMA_NONE;
   const bool use_mask = (c.flags & (SFR_F_MASK | SFR_F_MASK_AFTER_CLIP)) != 0;
@@ -287,25 +291,79 @@ void fill_ema_consts(UpdateConsts& c, int ema_mode, double a) {
   }
 }
 
+// Scalars exactly as torch's Python forms them (double), rounded to fp32 where the ATen kernel would
+// round them.  __host__ __device__: the device twin serves graph-replayable launches (device pow() is
+// within 2 ulp of glibc's in double, far below the fp32 rounding that follows).
+__host__ __device__ inline UpdateConsts make_update_consts(const sfr_update_args& a, int64_t step_i,
+                                                           bool has_momentum) {
+  UpdateConsts c{};
+  c.flags = a.flags;
+  c.has_wd = a.weight_decay != 0.0;
+  c.has_momentum = has_momentum;
+  c.max_norm = (float)a.clip_max_norm;
+  c.wd = (float)a.weight_decay;
+  if (a.opt == SFR_OPT_SGD) {
+    c.neg_lr = (float)(-a.lr);
+    c.momentum = (float)a.momentum;
+    c.one_m_damp = (float)(1.0 - a.dampening);
+  } else {
+    const double step = (double)step_i;
+    const double bc1 = 1.0 - pow(a.beta1, step);        // 1 - beta1 ** step
+    const double bc2 = 1.0 - pow(a.beta2, step);        // 1 - beta2 ** step
+    const double step_size = a.lr / bc1;                // lr / bias_correction1
+    c.neg_step_size = (float)(-step_size);
+    c.bc2_sqrt = (float)pow(bc2, 0.5);                  // bias_correction2 ** 0.5
+    c.lerp_w = (float)(1.0 - a.beta1);
+    c.beta2 = (float)a.beta2;
+    c.one_m_beta2 = (float)(1.0 - a.beta2);
+    c.eps = (float)a.eps;
+    c.decay_mul = (float)(1.0 - a.lr * a.weight_decay);
+  }
+  // Python computes (1 - a) in double; torch rounds each scalar to fp32 when the op runs.
+  if (a.ema_mode == SFR_EMA_DDPM) {             // (1.0 - mu) * p + mu * s
+    c.ema_c1 = (float)(1.0 - a.ema_a);
+    c.ema_c2 = (float)a.ema_a;
+  } else if (a.ema_mode == SFR_EMA_DIT) {       // s.mul_(d).add_(p, alpha=1 - d)
+    c.ema_c1 = (float)a.ema_a;
+    c.ema_c2 = (float)(1.0 - a.ema_a);
+  } else if (a.ema_mode == SFR_EMA_SLOWFAST) {  // (1 - b) * prev + b * p
+    c.ema_c1 = (float)(1.0 - a.ema_a);
+    c.ema_c2 = (float)a.ema_a;
+  }
+  return c;
+}
+
+__global__ void update_consts_kernel(sfr_update_args a, bool has_momentum, long long* step_counter,
+                                     UpdateConsts* out) {
+  const long long step = ++(*step_counter);       // optimizer state['step'] lives on the device
+  UpdateConsts c = make_update_consts(a, step, has_momentum);
+  if (a.opt == SFR_OPT_SGD && has_momentum) {
+    // first use of the momentum buffer (buf = clone(grad)) is decided by the device counter too
+    if (step == 1) c.flags |= SFR_F_SGD_FIRST_STEP; else c.flags &= ~SFR_F_SGD_FIRST_STEP;
+  }
+  *out = c;
+}
+
 template <int OPT, int EMA>
 void launch_update_gt(int gt, int grid, cudaStream_t s, float* p, void* g, float* m, float* v,
                       const uint8_t* mask, float* ema, void* p_bf16, int64_t n,
-                      const UpdateConsts& c, const double* clip_sumsq) {
+                      const UpdateConsts& c, const UpdateConsts* c_dev, const double* clip_sumsq) {
   if (gt == SFR_F32)
-    fused_update_kernel<OPT, EMA, SFR_F32><<<grid, kThreads, 0, s>>>(p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq);
+    fused_update_kernel<OPT, EMA, SFR_F32><<<grid, kThreads, 0, s>>>(p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq);
   else
-    fused_update_kernel<OPT, EMA, SFR_BF16><<<grid, kThreads, 0, s>>>(p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq);
+    fused_update_kernel<OPT, EMA, SFR_BF16><<<grid, kThreads, 0, s>>>(p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq);
 }
 
 template <int OPT>
 void launch_update_ema(int ema_mode, int gt, int grid, cudaStream_t s, float* p, void* g,
                        float* m, float* v, const uint8_t* mask, float* ema, void* p_bf16,
-                       int64_t n, const UpdateConsts& c, const double* clip_sumsq) {
+                       int64_t n, const UpdateConsts& c, const UpdateConsts* c_dev,
+                       const double* clip_sumsq) {
   switch (ema_mode) {
-    case SFR_EMA_DDPM: launch_update_gt<OPT, SFR_EMA_DDPM>(gt, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq); break;
-    case SFR_EMA_DIT: launch_update_gt<OPT, SFR_EMA_DIT>(gt, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq); break;
-    case SFR_EMA_SLOWFAST: launch_update_gt<OPT, SFR_EMA_SLOWFAST>(gt, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq); break;
-    default: launch_update_gt<OPT, SFR_EMA_NONE>(gt, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq); break;
+    case SFR_EMA_DDPM: launch_update_gt<OPT, SFR_EMA_DDPM>(gt, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq); break;
+    case SFR_EMA_DIT: launch_update_gt<OPT, SFR_EMA_DIT>(gt, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq); break;
+    case SFR_EMA_SLOWFAST: launch_update_gt<OPT, SFR_EMA_SLOWFAST>(gt, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq); break;
+    default: launch_update_gt<OPT, SFR_EMA_NONE>(gt, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq); break;
   }
 }
 
@@ -340,6 +398,7 @@ extern "C" int sfr_masked_sumsq(const void* g, int g_dtype, const uint8_t* mask,
 extern "C" int sfr_fused_update(float* p, void* g, float* m, float* v, const uint8_t* mask,
                                 float* ema, void* p_bf16, int64_t n,
                                 const sfr_update_args* a, const double* clip_sumsq,
+                                long long* step_counter, void* consts_scratch,
                                 sfr_stream_t stream) {
   using namespace sfr;
   SFR_REQUIRE_PTR(a);
@@ -351,7 +410,7 @@ extern "C" int sfr_fused_update(float* p, void* g, float* m, float* v, const uin
                          SFR_F_SGD_FIRST_STEP | SFR_F_WRITE_BF16;
   if (a->flags & ~known) return SFR_ERR_ARG;
   if ((a->flags & SFR_F_MASK) && (a->flags & SFR_F_MASK_AFTER_CLIP)) return SFR_ERR_ARG;
-  if (a->opt != SFR_OPT_SGD && a->step < 1) return SFR_ERR_ARG;
+  if (a->opt != SFR_OPT_SGD && a->step < 1 && step_counter == nullptr) return SFR_ERR_ARG;
   if (n == 0) return SFR_OK;
   const bool use_mask = (a->flags & (SFR_F_MASK | SFR_F_MASK_AFTER_CLIP)) != 0;
   const bool has_momentum = a->opt == SFR_OPT_SGD && a->momentum != 0.0;
@@ -371,45 +430,29 @@ extern "C" int sfr_fused_update(float* p, void* g, float* m, float* v, const uin
   SFR_REQUIRE_ALIGNED(p_bf16);
   if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
 
-  // Scalars exactly as torch's Python forms them (double), rounded to fp32 where the
-  // ATen kernel would round them.
-  UpdateConsts c{};
-  c.flags = a->flags;
-  c.has_wd = a->weight_decay != 0.0;
-  c.has_momentum = has_momentum;
-  c.max_norm = (float)a->clip_max_norm;
-  c.wd = (float)a->weight_decay;
-  if (a->opt == SFR_OPT_SGD) {
-    c.neg_lr = (float)(-a->lr);
-    c.momentum = (float)a->momentum;
-    c.one_m_damp = (float)(1.0 - a->dampening);
-  } else {
-    const double step = (double)a->step;
-    const double bc1 = 1.0 - pow(a->beta1, step);        // 1 - beta1 ** step
-    const double bc2 = 1.0 - pow(a->beta2, step);        // 1 - beta2 ** step
-    const double step_size = a->lr / bc1;                // lr / bias_correction1
-    c.neg_step_size = (float)(-step_size);
-    c.bc2_sqrt = (float)pow(bc2, 0.5);                   // bias_correction2 ** 0.5
-    c.lerp_w = (float)(1.0 - a->beta1);
-    c.beta2 = (float)a->beta2;
-    c.one_m_beta2 = (float)(1.0 - a->beta2);
-    c.eps = (float)a->eps;
-    c.decay_mul = (float)(1.0 - a->lr * a->weight_decay);
+  UpdateConsts c = make_update_consts(*a, a->step, has_momentum);
+  const UpdateConsts* c_dev = nullptr;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (step_counter != nullptr) {
+    // graph-replayable: ++(*step_counter) on the device, constants formed there
+    SFR_REQUIRE_PTR(consts_scratch);
+    if (!aligned16(consts_scratch)) return SFR_ERR_ALIGN;
+    update_consts_kernel<<<1, 1, 0, s>>>(*a, has_momentum, step_counter,
+                                         reinterpret_cast<UpdateConsts*>(consts_scratch));
+    c_dev = reinterpret_cast<const UpdateConsts*>(consts_scratch);
   }
-  fill_ema_consts(c, a->ema_mode, a->ema_a);
 
   const int64_t nvec = n >> 2;
   const int grid = persistent_grid((nvec + kThreads - 1) / kThreads, kUpdCtasPerSm * 8);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (a->opt) {
     case SFR_OPT_SGD:
-      launch_update_ema<SFR_OPT_SGD>(a->ema_mode, a->g_dtype, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq);
+      launch_update_ema<SFR_OPT_SGD>(a->ema_mode, a->g_dtype, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq);
       break;
     case SFR_OPT_ADAM:
-      launch_update_ema<SFR_OPT_ADAM>(a->ema_mode, a->g_dtype, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq);
+      launch_update_ema<SFR_OPT_ADAM>(a->ema_mode, a->g_dtype, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq);
       break;
     default:
-      launch_update_ema<SFR_OPT_ADAMW>(a->ema_mode, a->g_dtype, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, clip_sumsq);
+      launch_update_ema<SFR_OPT_ADAMW>(a->ema_mode, a->g_dtype, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq);
       break;
   }
   SFR_LAUNCH_STATUS();

@@ -57,9 +57,14 @@ def tie_bases(local_eq_counts: Sequence[int]) -> List[int]:
 
 
 class ShardGroup:
-    """A process group plus the shard arithmetic of one flat vector."""
+    """A process group plus the shard arithmetic of one flat vector.
 
-    def __init__(self, n_total: int, group=None, align: int = 16):
+    padded_len: length of the (padded) flat buffers, a multiple of world x align.  When given, shard r
+    is the r-th EQUAL slice of the padded buffer clipped to [0, n_total): reduce-scatter and all-gather
+    then work in place on equal chunks, while kernels only ever see the valid elements.
+    """
+
+    def __init__(self, n_total: int, group=None, align: int = 16, padded_len: Optional[int] = None):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.group = group
@@ -67,8 +72,21 @@ class ShardGroup:
         self.rank = dist.get_rank(group)
         self.n_total = int(n_total)
         self.align = align
-        self.bounds = [shard_bounds(self.n_total, self.world, r, align) for r in range(self.world)]
+        self.per = None
+        if padded_len is None:
+            self.bounds = [shard_bounds(self.n_total, self.world, r, align) for r in range(self.world)]
+        else:
+            if padded_len < self.n_total or padded_len % (self.world * align):
+                raise ValueError("padded_len must be >= n_total and a multiple of world * align")
+            self.per = padded_len // self.world
+            self.bounds = [(min(r * self.per, self.n_total), min((r + 1) * self.per, self.n_total))
+                           for r in range(self.world)]
         self.lo, self.hi = self.bounds[self.rank]
+        self._nccl = dist.get_backend(group) == "nccl"
+
+    @staticmethod
+    def pad_multiple(world: int, align: int = 16) -> int:
+        return world * align
 
     @property
     def n_local(self) -> int:
@@ -84,13 +102,32 @@ class ShardGroup:
         """Combine the per-rank gradients of a data-parallel backward pass; returns this rank's shard.
         (all-reduce: every rank keeps the full summed gradient, as DataParallel's reduce_add leaves on
         GPU 0; the sharded update only reads its slice.)"""
-        self.all_reduce_(g_full)
-        if average:
-            g_full.div_(self.world)
+        if average and self._nccl:
+            dist.all_reduce(g_full, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            self.all_reduce_(g_full)
+            if average:
+                g_full.div_(self.world)
         return self.local(g_full)
 
+    def reduce_scatter_gradients_(self, g_padded: torch.Tensor, average: bool = True) -> torch.Tensor:
+        """Sharded update only needs this rank's slice of the reduced gradient: reduce-scatter moves
+        half the bytes of an all-reduce.  In place on the padded gradient buffer (equal chunks)."""
+        if self.per is None:
+            raise RuntimeError("reduce_scatter needs a ShardGroup built with padded_len")
+        out = g_padded[self.rank * self.per:(self.rank + 1) * self.per]
+        op = dist.ReduceOp.AVG if (average and self._nccl) else dist.ReduceOp.SUM
+        dist.reduce_scatter_tensor(out, g_padded, op=op, group=self.group)
+        if average and not self._nccl:
+            out.div_(self.world)
+        return out[:self.n_local]
+
     def all_gather_params_(self, p_full: torch.Tensor) -> None:
-        """Every rank updated p_full[lo:hi]; make the whole vector consistent again."""
+        """Every rank updated its shard of p_full; make the whole vector consistent again."""
+        if self.per is not None and p_full.numel() == self.per * self.world:
+            dist.all_gather_into_tensor(p_full, p_full[self.rank * self.per:(self.rank + 1) * self.per],
+                                        group=self.group)
+            return
         shards = [p_full[lo:hi] for lo, hi in self.bounds]
         if len({s.numel() for s in shards}) == 1 and p_full.is_cuda:
             dist.all_gather_into_tensor(p_full[:shards[0].numel() * self.world], shards[self.rank], group=self.group)

@@ -63,6 +63,9 @@ class HotPath:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.zero_count = torch.zeros(capi.MAX_THRESHOLDS, dtype=torch.int64, device=self.device)
         self._select = None
+        # replay-safe mode (CUDA graphs): the optimizer step counter lives on the device
+        self.step_dev: Optional[torch.Tensor] = None
+        self._consts_dev: Optional[torch.Tensor] = None
         # optional probe called with a label right after each kernel launch (bench.py records a
         # CUDA event there to attribute device time per kernel); None on the normal path
         self.trace = None
@@ -70,6 +73,22 @@ class HotPath:
     def _t(self, label: str) -> None:
         if self.trace is not None:
             self.trace(label)
+
+    def enable_graph_replay(self) -> None:
+        """Make forget_step / remain_step safe to capture in a CUDA graph and replay: the step count
+        (Adam bias corrections, SGD's first-step momentum-buffer init) moves to a device counter that a
+        one-thread kernel advances on every launch/replay.  Allocates everything the steps need up front
+        (nothing may be allocated during capture)."""
+        if self.step_dev is None:
+            self.step_dev = torch.full((1,), self.step_count, dtype=torch.int64, device=self.device)
+            self._consts_dev = torch.zeros(128, dtype=torch.uint8, device=self.device)
+        sgd = self.opt.kind == "sgd"
+        if not sgd or self.opt.momentum != 0.0:
+            self.buffer("m")
+        if not sgd:
+            self.buffer("v")
+        if self.ema_mode != "none":
+            self.buffer("slow")
 
     # ---- lazily allocated role buffers ------------------------------------------------------------
     def buffer(self, role: str, dtype=torch.float32) -> torch.Tensor:
@@ -252,7 +271,7 @@ class HotPath:
         if p_bf16 is not None:
             flags |= capi.F_WRITE_BF16
         sgd = self.opt.kind == "sgd"
-        if sgd and self.opt.momentum != 0.0 and not self.has("m"):
+        if self.step_dev is None and sgd and self.opt.momentum != 0.0 and not self.has("m"):
             flags |= capi.F_SGD_FIRST_STEP      # torch creates momentum_buffer = clone(grad) on first use
         clip = None
         if max_norm is not None:
@@ -267,7 +286,8 @@ class HotPath:
         use_ema = ema and self.ema_mode != "none"
         capi.fused_update(p, g, None if (sgd and self.opt.momentum == 0.0) else self.m,
                           None if sgd else self.v, mask, self.slow if use_ema else None, a,
-                          clip_sumsq=clip, p_bf16=p_bf16)
+                          clip_sumsq=clip, p_bf16=p_bf16, step_counter=self.step_dev,
+                          consts_scratch=self._consts_dev)
         self._t("fused_update_ema" if use_ema else "fused_update")
 
     def forget_step(self, p: torch.Tensor, g: torch.Tensor, *, mask: Optional[torch.Tensor] = None,

@@ -118,13 +118,23 @@ def shard_bounds(n: int, world: int, rank: int, align: int = 16) -> Tuple[int, i
 class FlatParams:
     """Device buffers of the hot path for one model, with per-name views.
 
-    `adopt(model)` re-points every trainable `param.data` (and optionally `param.grad`) into the
-    flat `p` (`g`) buffer, so autograd reads weights from and accumulates gradients into the
-    flat vectors directly: no gather before, no scatter after the kernels.
+    The constructor re-points every trainable `param.data` (and `param.grad`) into flat buffers, so
+    autograd reads weights from and accumulates gradients into the flat vectors directly: no gather
+    before, no scatter after the kernels.
+
+    fp32 model (the reference's only mode): `p` (fp32) IS the module weights, `g` (fp32) the grads.
+    bf16 model (BASELINE config 3, an extension — the reference never uses reduced precision): the
+    module weights are views into `p_work` (bf16) and the grads views into `g` (bf16); `p` is the fp32
+    MASTER copy the kernels update (writing the bf16 working copy back in the same pass), and the
+    optimizer state / Fisher / EMA stay fp32.
+
+    pad_multiple: allocate the flat buffers with a length rounded up to this many elements (the views
+    and every kernel still cover exactly n elements) so that equal-sized shards exist for
+    reduce-scatter / all-gather; the tail [n, n_padded) is never part of the logical vector.
     """
 
     def __init__(self, model: torch.nn.Module, device=None, *, grads_as_views: bool = True,
-                 grad_dtype: torch.dtype = torch.float32):
+                 grad_dtype: Optional[torch.dtype] = None, pad_multiple: int = 1):
         named = list(model.named_parameters())
         train = [(n, p) for n, p in named if p.requires_grad]
         frozen = [(n, p) for n, p in named if not p.requires_grad]
@@ -134,21 +144,49 @@ class FlatParams:
         if device is None:
             device = train[0][1].device if train else torch.device("cuda")
         self.device = torch.device(device)
+        dtypes = {p.dtype for _, p in train}
+        if len(dtypes) > 1:
+            raise ValueError(f"mixed parameter dtypes {dtypes}")
+        self.param_dtype = dtypes.pop() if dtypes else torch.float32
+        if self.param_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError(f"parameter dtype {self.param_dtype} not supported (fp32 | bf16)")
+        if grad_dtype is None:
+            grad_dtype = self.param_dtype
+        if not grads_as_views:
+            grad_dtype = torch.float32          # the gather kernel widens whatever autograd produced
         n = self.layout.numel
         self.n = n
-        self.p = torch.empty(n, dtype=torch.float32, device=self.device)
-        self.g = torch.zeros(n, dtype=grad_dtype, device=self.device)
+        self.n_padded = (n + pad_multiple - 1) // pad_multiple * pad_multiple
+        self.p_padded = torch.zeros(self.n_padded, dtype=torch.float32, device=self.device)
+        self.g_padded = torch.zeros(self.n_padded, dtype=grad_dtype, device=self.device)
+        self.p = self.p_padded[:n]
+        self.g = self.g_padded[:n]
+        self.p_work_padded = (torch.zeros(self.n_padded, dtype=torch.bfloat16, device=self.device)
+                              if self.param_dtype == torch.bfloat16 else None)
+        self.p_work = None if self.p_work_padded is None else self.p_work_padded[:n]
+        weights = self.p if self.p_work is None else self.p_work        # what the module sees
         self.frozen = torch.empty(self.frozen_layout.numel, dtype=torch.float32, device=self.device)
+        self.frozen_work = (torch.empty(self.frozen_layout.numel, dtype=self.param_dtype, device=self.device)
+                            if self.param_dtype != torch.float32 else None)
+        views_ok = grads_as_views and grad_dtype == self.param_dtype
         with torch.no_grad():
             for seg, (_, prm) in zip(self.layout, train):
-                self.p[seg.offset:seg.offset + seg.numel].copy_(prm.detach().reshape(-1))
-                prm.data = self.p[seg.offset:seg.offset + seg.numel].view(seg.shape)
-                if grads_as_views and grad_dtype == torch.float32:
-                    prm.grad = self.g[seg.offset:seg.offset + seg.numel].view(seg.shape)
+                sl = slice(seg.offset, seg.offset + seg.numel)
+                self.p[sl].copy_(prm.detach().reshape(-1))              # fp32 master (exact widening)
+                if self.p_work is not None:
+                    self.p_work[sl].copy_(prm.detach().reshape(-1))
+                prm.data = weights[sl].view(seg.shape)
+                if views_ok:
+                    prm.grad = self.g[sl].view(seg.shape)
             for seg, (_, prm) in zip(self.frozen_layout, frozen):
-                self.frozen[seg.offset:seg.offset + seg.numel].copy_(prm.detach().reshape(-1))
-                prm.data = self.frozen[seg.offset:seg.offset + seg.numel].view(seg.shape)
-        self.grads_as_views = grads_as_views and grad_dtype == torch.float32
+                sl = slice(seg.offset, seg.offset + seg.numel)
+                self.frozen[sl].copy_(prm.detach().reshape(-1))
+                if self.frozen_work is not None:
+                    self.frozen_work[sl].copy_(prm.detach().reshape(-1))
+                    prm.data = self.frozen_work[sl].view(seg.shape)
+                else:
+                    prm.data = self.frozen[sl].view(seg.shape)
+        self.grads_as_views = views_ok
         self._train_params = [p for _, p in train]
         self._gather_tables = None
 
@@ -185,8 +223,6 @@ class FlatParams:
             self._gather_tables = (offs.to(self.device), torch.tensor(sizes, dtype=torch.int64).to(self.device))
         offs_d, sizes_d = self._gather_tables
         srcs_d = torch.tensor(srcs, dtype=torch.int64).to(self.device, non_blocking=False)
-        if self.g.dtype != torch.float32:
-            self.g = torch.zeros(self.n, dtype=torch.float32, device=self.device)
         capi.gather_segments(self.g, srcs_d, offs_d, sizes_d,
                              capi.F32 if dt == torch.float32 else capi.BF16, self.n)
         return self.g

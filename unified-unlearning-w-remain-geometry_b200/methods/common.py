@@ -101,11 +101,12 @@ class ModelHotPath:
     def forget_step(self, *, use_mask: bool = True, max_norm: Optional[float] = None, lr: Optional[float] = None,
                     mask_order: str = "mask_then_clip") -> None:
         self.hp.forget_step(self.flat.p, self.grads(), use_mask=use_mask, max_norm=max_norm, lr=lr,
-                            mask_order=mask_order, zero_grad=self.flat.grads_as_views)
+                            mask_order=mask_order, zero_grad=self.flat.grads_as_views,
+                            p_bf16=self.flat.p_work)
 
     def remain_step(self, *, max_norm: Optional[float] = None, lr: Optional[float] = None, ema: bool = True) -> None:
         self.hp.remain_step(self.flat.p, self.grads(), max_norm=max_norm, lr=lr, ema=ema,
-                            zero_grad=self.flat.grads_as_views)
+                            zero_grad=self.flat.grads_as_views, p_bf16=self.flat.p_work)
         if ema and self.frozen_slow is not None:
             self.hp.ema_only(self.flat.frozen, self.frozen_slow)
 
