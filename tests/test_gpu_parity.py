@@ -535,3 +535,57 @@ def test_k3_cuda_graph_replay_advances_device_step(sfr, dev, opt, kw, ema_mode, 
     assert close(p, ref.flat("p"))
     if ema_mode != "none":
         assert close(hp.slow, ref.flat("slow"))
+
+
+# =============================================================================== own bounds check
+def _guarded(dev, n, dtype, fill):
+    """A 16-byte-aligned n-element view in the middle of a larger allocation whose remainder holds a
+    sentinel: any out-of-bounds WRITE of a kernel lands in a guard zone (compute-sanitizer is closed on
+    this pool)."""
+    item = torch.empty(0, dtype=dtype).element_size()
+    guard = 4096 // item
+    n_alloc = (n + 15) // 16 * 16
+    buf = torch.full((guard + n_alloc + guard,), fill, dtype=dtype, device=dev)
+    view = buf[guard:guard + n]
+    return buf, view, guard
+
+
+def _guards_intact(buf, view_n, guard, fill):
+    head, tail = buf[:guard], buf[guard + view_n:]
+    return bool((head == fill).all()) and bool((tail == fill).all())
+
+
+@pytest.mark.parametrize("n", [1, 3, 5, 1023, 4097, 8191, 8193, 100_003])
+def test_no_out_of_bounds_writes(sfr, dev, n):
+    capi = sfr.capi
+    g = gen(n)
+    S = 12345.0
+    bufs = {}
+    for name in ("acc", "p", "m", "v", "ema", "gz"):
+        bufs[name] = _guarded(dev, n, torch.float32, S)
+        bufs[name][1].copy_(torch.randn(n, generator=g) * 0.01)
+    bufs["v"][1].abs_()
+    mb, mask, mg = _guarded(dev, n, torch.uint8, 77)
+    tb, topk, tg = _guarded(dev, n, torch.uint8, 77)
+    pb, p16, pg = _guarded(dev, n, torch.bfloat16, 3.0)
+    grad = (torch.randn(n, generator=g) * 0.1).to(dev)
+    ff = torch.randn(n, generator=g).pow(2).to(dev)
+    rf = torch.randn(n, generator=g).pow(2).to(dev)
+    capi.fisher_accum(bufs["acc"][1], grad, 3.0)
+    capi.ratio_mask(ff, rf, 1.0, mask)
+    hp = sfr.HotPath(n, dev, sfr.OptConfig(kind="adamw", lr=1e-3, weight_decay=0.01), ema_mode="dit", ema_a=0.99)
+    hp.set_buffer("m", bufs["m"][1]); hp.set_buffer("v", bufs["v"][1]); hp.set_buffer("slow", bufs["ema"][1])
+    hp.set_buffer("mask", mask)
+    bufs["gz"][1].copy_(grad)
+    hp.forget_step(bufs["p"][1], bufs["gz"][1], max_norm=1.0, zero_grad=True, p_bf16=p16)
+    bufs["gz"][1].copy_(grad)
+    hp.remain_step(bufs["p"][1], bufs["gz"][1], ema=True, zero_grad=True, p_bf16=p16)
+    quant = (grad * 8).round() / 8                      # heavy ties -> ordered apply path
+    hp.topk_mask(quant, max(1, n // 3), out=topk)
+    hp.topk_mask(grad, n // 2, out=topk)
+    capi.ewc_penalty(bufs["p"][1], bufs["ema"][1], ff, bufs["gz"][1], 2.0)
+    hp.proximal_shrink(bufs["p"][1], bufs["ema"][1], max(1, n // 2))
+    torch.cuda.synchronize()
+    for name, (buf, view, guard) in bufs.items():
+        assert _guards_intact(buf, n, guard, S), f"{name}: write outside [0, n)"
+    assert _guards_intact(mb, n, mg, 77) and _guards_intact(tb, n, tg, 77) and _guards_intact(pb, n, pg, 3.0)
