@@ -232,3 +232,40 @@ def test_padded_flat_params_views_and_length(dev):
     fp = sfr.FlatParams(model, dev, pad_multiple=128)
     assert fp.n == 554 and fp.n_padded == 640 and fp.p.numel() == 554
     assert fp.p.data_ptr() == fp.p_padded.data_ptr() and int(fp.p_padded[554:].abs().sum()) == 0
+
+
+def test_per_sample_fim_vmap_producer_matches_retain_graph_loop(dev):
+    """the vmapped per-sample-gradient producer + K1 rows against the reference's
+    `loss[i].backward(retain_graph=True)` loop and `F += tmp_i**2 / |D|` (runners/diffusion.py:326-344)."""
+    from torch.func import functional_call
+    from sfron_b200.methods.diffusion import DiffusionUnlearner, adaptive_loss, per_sample_grad_rows
+    torch.manual_seed(0)
+    model = TinyNet().to(dev)
+    x = torch.randn(6, 3, 8, 8, device=dev)
+    y = torch.randint(0, 10, (6,), device=dev)
+    # reference form: per-sample losses, one backward per sample over a retained graph
+    loss = torch.nn.functional.cross_entropy(model(x), y, reduction="none")
+    ref_rows = []
+    for i in range(6):
+        model.zero_grad()
+        loss[i].backward(retain_graph=i != 5)
+        ref_rows.append(torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone())
+    model.zero_grad()
+    ref_rows = torch.stack(ref_rows)
+    want = torch.zeros(ref_rows.shape[1], device=dev)
+    for r in ref_rows:
+        want += r ** 2 / 50
+
+    def one_sample_loss(pb, xi, yi):
+        out = functional_call(model, pb, (xi.unsqueeze(0),))
+        return torch.nn.functional.cross_entropy(out, yi.unsqueeze(0))
+
+    un = DiffusionUnlearner(model, "ddpm")
+    rows = per_sample_grad_rows(model, one_sample_loss, (x, y))
+    assert rows.shape == ref_rows.shape and torch.allclose(rows, ref_rows, rtol=1e-4, atol=1e-7)
+    fim = un.save_fim([rows[:4], rows[4:]], dataset_len=50)
+    assert torch.allclose(fim, want, rtol=1e-4, atol=1e-12)
+    # adaptive re-weighting keeps the batch mean scale and up-weights low-loss samples
+    l = torch.tensor([0.5, 1.0, 2.0], device=dev)
+    w = adaptive_loss(l, 3, gamma=1.0, eps=1e-8, keepdim=True) / l
+    assert torch.allclose(w.sum(), torch.tensor(3.0, device=dev)) and w[0] > w[1] > w[2]

@@ -57,6 +57,45 @@ def preset(family: str, **over) -> FamilyPreset:
 LossFn = Callable[[int], torch.Tensor]
 
 
+def adaptive_loss(ori_loss: torch.Tensor, size: int, gamma: float = 1.0, eps: float = 1e-15,
+                  keepdim: bool = False) -> torch.Tensor:
+    """Adaptive forget-loss re-weighting: `coef = 1 / (loss**gamma + eps)`, normalised, times the batch
+    size.  Stays in PyTorch (it is part of the loss graph).  eps differs per sub-project:
+    1e-15 Classification sfron.py:57 and DiT/forget.py:44; 1e-8 DDPM/functions/losses.py:63."""
+    coef = 1 / (torch.pow(ori_loss.detach().clone(), gamma) + eps)
+    ad_loss = (coef / coef.sum()) * ori_loss * size
+    return ad_loss if keepdim else ad_loss.mean(dim=0)
+
+
+def per_sample_grad_rows(model: torch.nn.Module, per_sample_loss: Callable, batch: tuple) -> torch.Tensor:
+    """[B, n] flat per-sample gradients in ONE vmapped backward pass — the producer for K1's `rows > 1`
+    form.  Replaces DDPM save_fim's `for i in range(bs): loss[i].backward(retain_graph=True)` loop
+    (runners/diffusion.py:326-333), which runs B backward passes over a retained graph.
+
+    per_sample_loss(params_and_buffers: dict, *sample) -> scalar loss of ONE sample, written with
+    torch.func.functional_call.  Rows follow the flat layout (trainable parameters, named_parameters order).
+    """
+    from torch.func import functional_call, grad, vmap  # noqa: F401  (functional_call is for the caller)
+    params = {n: p.detach() for n, p in model.named_parameters() if p.requires_grad}
+    frozen = {n: p.detach() for n, p in model.named_parameters() if not p.requires_grad}
+    buffers = {n: b for n, b in model.named_buffers()}
+
+    def one(train_params, *sample):
+        return per_sample_loss({**train_params, **frozen, **buffers}, *sample)
+
+    grads = vmap(grad(one), in_dims=(None,) + (0,) * len(batch))(params, *batch)
+    b = batch[0].shape[0]
+    n = sum(p.numel() for p in params.values())
+    stride = (n + 7) // 8 * 8                       # every row 16-byte aligned (fp32 and bf16)
+    rows = torch.empty(b, stride, dtype=next(iter(grads.values())).dtype, device=batch[0].device)
+    off = 0
+    for name in params:
+        g = grads[name].reshape(b, -1)
+        rows[:, off:off + g.shape[1]].copy_(g)
+        off += g.shape[1]
+    return rows[:, :n]
+
+
 class DiffusionUnlearner:
     def __init__(self, model: torch.nn.Module, family: str = "dit", *, device=None, **preset_overrides):
         self.family = family
