@@ -13,7 +13,7 @@ Only what the path needs lives here:
   methods/   drop-in mirrors of the reference's entry points
 """
 from . import capi, flat, formats  # noqa: F401
-from .engine import HotPath, OptConfig  # noqa: F401
+from .engine import HostGradientFeeder, HotPath, OptConfig  # noqa: F401
 from .flat import FlatLayout, FlatParams, shard_bounds  # noqa: F401
 
-__all__ = ["capi", "flat", "formats", "HotPath", "OptConfig", "FlatLayout", "FlatParams", "shard_bounds"]
+__all__ = ["capi", "flat", "formats", "HotPath", "HostGradientFeeder", "OptConfig", "FlatLayout", "FlatParams", "shard_bounds"]

@@ -316,3 +316,60 @@ class HotPath:
     def ema_only(self, p: torch.Tensor, slow: torch.Tensor) -> None:
         """EMA of parameters the optimizer never touches (frozen DiT pos_embed, DiT/forget.py:58-62)."""
         capi.ema_update(p, slow, _EMA_CODES[self.ema_mode], self.ema_a)
+
+
+class HostGradientFeeder:
+    """Host-buffer entry of the path: gradients that arrive in PINNED HOST memory (a host-side or
+    off-device producer — the direction in which the reference moves them every step, D2H then CPU math)
+    are prefetched to the device on a copy stream, double-buffered, so the H2D of step i+1 overlaps the
+    kernels of step i.  Steady state is bound by the PCIe copy alone.
+
+        feeder = HostGradientFeeder(n, device, slots=("forget", "remain"))
+        feeder.submit(forget=host_gf, remain=host_gr)            # step 0
+        for step in ...:
+            g = feeder.acquire()                                 # device views of this step's gradients
+            feeder.submit(forget=..., remain=...)                # next step's copy starts now
+            hot_path.fisher_accumulate("forget", g["forget"], L) ; ...
+            feeder.release()                                     # buffers may be overwritten
+    """
+
+    def __init__(self, n: int, device, slots: Sequence[str] = ("forget", "remain"),
+                 dtype: torch.dtype = torch.float32, depth: int = 2):
+        self.device = torch.device(device)
+        self.slots = tuple(slots)
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.buffers = [{s: torch.empty(n, dtype=dtype, device=self.device) for s in self.slots}
+                        for _ in range(depth)]
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [torch.cuda.Event() for _ in range(depth)]
+        self._submitted = 0
+        self._acquired = 0
+        self.bytes_per_step = n * torch.empty(0, dtype=dtype).element_size() * len(self.slots)
+
+    def submit(self, **host_tensors: torch.Tensor) -> None:
+        if self._submitted - self._acquired >= self.depth:
+            raise RuntimeError("feeder full: acquire()/release() a step before submitting another")
+        i = self._submitted % self.depth
+        with torch.cuda.stream(self.copy_stream):
+            if self._submitted >= self.depth:
+                self.copy_stream.wait_event(self.free[i])       # the kernels that read this buffer are done
+            for s in self.slots:
+                h = host_tensors[s]
+                if not h.is_pinned():
+                    raise ValueError(f"{s}: host gradient buffers must be pinned for an asynchronous copy")
+                self.buffers[i][s].copy_(h, non_blocking=True)
+            self.ready[i].record(self.copy_stream)
+        self._submitted += 1
+
+    def acquire(self) -> Dict[str, torch.Tensor]:
+        if self._acquired >= self._submitted:
+            raise RuntimeError("nothing submitted")
+        i = self._acquired % self.depth
+        torch.cuda.current_stream(self.device).wait_event(self.ready[i])
+        self._current = i
+        self._acquired += 1
+        return self.buffers[i]
+
+    def release(self) -> None:
+        self.free[self._current].record(torch.cuda.current_stream(self.device))

@@ -127,7 +127,8 @@ class ModelHotPath:
                 n_frozen_before.append(seen)
             else:
                 seen += 1
-        return formats.adam_state_dict(self.layout, self.hp.m, self.hp.v, self.hp.step_count, lr=o.lr,
+        step = self.hp.step_count if self.hp.step_dev is None else int(self.hp.step_dev)
+        return formats.adam_state_dict(self.layout, self.hp.m, self.hp.v, step, lr=o.lr,
                                        betas=(o.beta1, o.beta2), eps=o.eps, weight_decay=o.weight_decay,
                                        n_frozen_before=n_frozen_before, param_count=len(self.flat.all_names),
                                        decoupled=o.kind == "adamw")
