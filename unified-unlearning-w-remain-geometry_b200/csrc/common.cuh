@@ -3,9 +3,15 @@
 // Every kernel on this path is an HBM-bound stream over a flat parameter shard:
 //   * 128-bit coalesced accesses (one float4 per thread per access, a warp covers
 //     512 contiguous bytes), several independent accesses in flight per thread;
-//   * streaming cache hints (ld.global.cs / st.global.cs): every byte is touched once
-//     per launch, so nothing is worth keeping in L1 and L2 should evict it first;
-//   * persistent grid = SMs x resident CTAs, tiles handed out grid-stride;
+//   * cache policy by stream role, measured on B200 (tools/tune/tune_stream.cu, tools/sweep.py):
+//     read-modify-write kernels (K1, K2a, K3, EWC, shrink) use PLAIN ld.global / st.global — the
+//     evict-first / no-allocate hints cost them 3-13 %; READ-ONLY kernels (clip norm, select
+//     histograms, tie count, apply's key reads) use ld.global.cs (evict-first), which is 8-15 %
+//     faster for them than default caching;
+//   * small CTAs (128 threads) and LARGE grids — one tile per CTA for the update shape, SMs x 16 x 32
+//     CTAs for the two-read-one-write shape: the hardware block scheduler keeps all SMs on one
+//     moving window of addresses; measured 6.8-6.9 TB/s vs 5.7-6.1 TB/s for a persistent
+//     SMs x resident-CTAs grid-stride loop (same sweep);
 //   * reductions: warp shuffle -> shared memory -> ONE atomic per CTA.
 // No fast-math: the file is compiled with -fmad=false and uses explicit
 // __f*_rn / __fmaf_rn so the rounding sequence is exactly the one documented in
@@ -42,19 +48,68 @@ inline int persistent_grid(int64_t tiles, int ctas_per_sm) {
   return (int)(tiles < cap ? tiles : cap);
 }
 
+// One tile per CTA (every kernel still loops grid-stride, so the 2^31-1 cap is harmless).
+inline int full_grid(int64_t tiles) {
+  if (tiles < 1) tiles = 1;
+  return (int)(tiles < 2147483647LL ? tiles : 2147483647LL);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// ---- streaming vector access ---------------------------------------------------
-__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
-__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
-__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
-__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+// ---- vector access ---------------------------------------------------------------
+// ld_stream / st_stream: streams of read-modify-write kernels (default caching).
+// ld_once: data a kernel reads exactly once and never writes (evict-first).
+__device__ __forceinline__ float4 ld_once(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ float ld_once(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return *p; }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { *p = v; }
+__device__ __forceinline__ float ld_stream(const float* p) { return *p; }
+__device__ __forceinline__ void st_stream(float* p, float v) { *p = v; }
 
 __device__ __forceinline__ float bf16_bits_to_f32(uint32_t b16) { return __uint_as_float(b16 << 16); }
 
 // Four consecutive gradients starting at element 4*vec, as fp32.
 template <int GT>
 __device__ __forceinline__ float4 load_g4(const void* g, int64_t vec) {
+  if constexpr (GT == SFR_F32) {
+    return *(reinterpret_cast<const float4*>(g) + vec);
+  } else {
+    uint2 raw = *(reinterpret_cast<const uint2*>(g) + vec);
+    float4 r;
+    r.x = bf16_bits_to_f32(raw.x & 0xffffu);
+    r.y = bf16_bits_to_f32(raw.x >> 16);
+    r.z = bf16_bits_to_f32(raw.y & 0xffffu);
+    r.w = bf16_bits_to_f32(raw.y >> 16);
+    return r;
+  }
+}
+template <int GT>
+__device__ __forceinline__ float load_g1(const void* g, int64_t i) {
+  if constexpr (GT == SFR_F32) {
+    return *(reinterpret_cast<const float*>(g) + i);
+  } else {
+    return bf16_bits_to_f32(*(reinterpret_cast<const unsigned short*>(g) + i));
+  }
+}
+template <int GT>
+__device__ __forceinline__ void zero_g4(void* g, int64_t vec) {
+  if constexpr (GT == SFR_F32) {
+    *(reinterpret_cast<float4*>(g) + vec) = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    *(reinterpret_cast<uint2*>(g) + vec) = make_uint2(0u, 0u);
+  }
+}
+template <int GT>
+__device__ __forceinline__ void zero_g1(void* g, int64_t i) {
+  if constexpr (GT == SFR_F32) {
+    reinterpret_cast<float*>(g)[i] = 0.f;
+  } else {
+    reinterpret_cast<unsigned short*>(g)[i] = 0;
+  }
+}
+
+template <int GT>
+__device__ __forceinline__ float4 load_g4_once(const void* g, int64_t vec) {
   if constexpr (GT == SFR_F32) {
     return __ldcs(reinterpret_cast<const float4*>(g) + vec);
   } else {
@@ -67,34 +122,13 @@ __device__ __forceinline__ float4 load_g4(const void* g, int64_t vec) {
     return r;
   }
 }
-template <int GT>
-__device__ __forceinline__ float load_g1(const void* g, int64_t i) {
-  if constexpr (GT == SFR_F32) {
-    return __ldcs(reinterpret_cast<const float*>(g) + i);
-  } else {
-    return bf16_bits_to_f32(__ldcs(reinterpret_cast<const unsigned short*>(g) + i));
-  }
-}
-template <int GT>
-__device__ __forceinline__ void zero_g4(void* g, int64_t vec) {
-  if constexpr (GT == SFR_F32) {
-    __stcs(reinterpret_cast<float4*>(g) + vec, make_float4(0.f, 0.f, 0.f, 0.f));
-  } else {
-    __stcs(reinterpret_cast<uint2*>(g) + vec, make_uint2(0u, 0u));
-  }
-}
-template <int GT>
-__device__ __forceinline__ void zero_g1(void* g, int64_t i) {
-  if constexpr (GT == SFR_F32) {
-    reinterpret_cast<float*>(g)[i] = 0.f;
-  } else {
-    reinterpret_cast<unsigned short*>(g)[i] = 0;
-  }
+__device__ __forceinline__ uint32_t load_mask4_once(const uint8_t* mask, int64_t vec) {
+  return __ldcs(reinterpret_cast<const unsigned int*>(mask) + vec);
 }
 
 // Four mask bytes (0/1) for elements 4*vec .. 4*vec+3.
 __device__ __forceinline__ uint32_t load_mask4(const uint8_t* mask, int64_t vec) {
-  return __ldcs(reinterpret_cast<const unsigned int*>(mask) + vec);
+  return *(reinterpret_cast<const unsigned int*>(mask) + vec);
 }
 __device__ __forceinline__ float mask_byte_to_f32(uint32_t packed, int lane) {
   return (float)((packed >> (8 * lane)) & 0xffu);

@@ -17,8 +17,8 @@
 namespace sfr {
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kUnroll = 2;
+constexpr int kThreads = 128;
+constexpr int kUnroll = 1;
 
 __device__ __forceinline__ float ewc_term(float f, float p, float ps, float lambda, float& gadd) {
   const float d = __fsub_rn(p, ps);
@@ -27,7 +27,7 @@ __device__ __forceinline__ float ewc_term(float f, float p, float ps, float lamb
   return __fmul_rn(f, __fmul_rn(d, d));  // F * d**2
 }
 
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 8)
 ewc_penalty_kernel(const float* __restrict__ p, const float* __restrict__ ps,
                    const float* __restrict__ fisher, float* __restrict__ g, int64_t n, float lambda,
                    double* __restrict__ penalty) {
@@ -89,7 +89,7 @@ __device__ __forceinline__ float shrink(float p, float p0, float thr) {
   return __fadd_rn(d, p0);                       // param += init_param
 }
 
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 8)
 soft_threshold_kernel(float* __restrict__ p, const float* __restrict__ p0, int64_t n,
                       const float* __restrict__ thr_dev) {
   const float thr = *thr_dev;
@@ -142,7 +142,7 @@ extern "C" int sfr_ewc_penalty(const float* p, const float* p_star, const float*
   if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
   const int64_t nvec = n >> 2;
   const int64_t tile = (int64_t)kThreads * kUnroll;
-  const int grid = persistent_grid((nvec + tile - 1) / tile, 4 * 4);
+  const int grid = persistent_grid((nvec + tile - 1) / tile, 16 * 128);
   ewc_penalty_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, p_star, fisher, g, n, lambda, penalty);
   SFR_LAUNCH_STATUS();
 }
@@ -168,7 +168,7 @@ extern "C" int sfr_soft_threshold(float* p, const float* p0, int64_t n, const fl
   SFR_REQUIRE_ALIGNED(p0);
   if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
   const int64_t nvec = n >> 2;
-  const int grid = persistent_grid((nvec + kThreads - 1) / kThreads, 4 * 8);
+  const int grid = persistent_grid((nvec + kThreads - 1) / kThreads, 16 * 128);
   soft_threshold_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, p0, n, threshold_dev);
   SFR_LAUNCH_STATUS();
 }

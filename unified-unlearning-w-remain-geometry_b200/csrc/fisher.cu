@@ -16,9 +16,10 @@
 namespace sfr {
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kCtasPerSm = 4;
-constexpr int kUnroll = 4;  // independent 128-bit loads in flight per stream per thread
+constexpr int kThreads = 128;
+constexpr int kCtasPerSm = 12;  // register cap 42; 16 resident when the variant needs <= 32
+constexpr int kUnroll = 2;      // independent 128-bit loads in flight per stream per thread
+constexpr int kGridWaves = 32;  // grid = SMs x 16 x 32 CTAs (tuned: tools/tune/tune_stream.cu)
 
 template <bool CLIP>
 __device__ __forceinline__ float fisher_term(float g, float coef, float divisor) {
@@ -101,7 +102,7 @@ extern "C" int sfr_fisher_accum(float* acc, const void* g, int g_dtype, int64_t 
 
   const int64_t nvec = n >> 2;
   const int64_t tile = (int64_t)kThreads * kUnroll;
-  const int grid = persistent_grid((nvec + tile - 1) / tile, kCtasPerSm);
+  const int grid = persistent_grid((nvec + tile - 1) / tile, 16 * kGridWaves);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool clip = clip_sumsq != nullptr;
 #define SFR_K1(GT, CL)                                                                  \

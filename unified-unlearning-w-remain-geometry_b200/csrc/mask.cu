@@ -15,9 +15,10 @@
 namespace sfr {
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kCtasPerSm = 4;
-constexpr int kUnroll = 4;
+constexpr int kThreads = 128;
+constexpr int kCtasPerSm = 8;
+constexpr int kUnroll = 2;
+constexpr int kGridWaves = 32;
 
 struct Thresholds {
   float v[SFR_MAX_THRESHOLDS];
@@ -67,8 +68,8 @@ ratio_mask_kernel(const float* __restrict__ ff, const float* __restrict__ rf, in
         const unsigned int b0 = q0 >= th.v[k], b1 = q1 >= th.v[k];
         const unsigned int b2 = q2 >= th.v[k], b3 = q3 >= th.v[k];
         ones[k] += b0 + b1 + b2 + b3;
-        __stcs(reinterpret_cast<unsigned int*>(masks + (int64_t)k * mask_stride) + v,
-               b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+        *(reinterpret_cast<unsigned int*>(masks + (int64_t)k * mask_stride) + v) =
+            b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
       }
     }
   }
@@ -103,7 +104,13 @@ int launch_ratio(const float* ff, const float* rf, int64_t n, const Thresholds& 
                  cudaStream_t s) {
   const int64_t nvec = n >> 2;
   const int64_t tile = (int64_t)kThreads * kUnroll;
-  const int grid = persistent_grid((nvec + tile - 1) / tile, kCtasPerSm);
+  // every CTA ends with T block reductions + T atomics (zero counts): give each at least 8 tiles
+  const int64_t ntiles = (nvec + tile - 1) / tile;
+  const int64_t by_work = ntiles / 8 > 1 ? ntiles / 8 : 1;
+  const int cap = persistent_grid(ntiles, 16 * kGridWaves);
+  const int floor_ = persistent_grid(ntiles, kCtasPerSm);
+  int grid = (int)(by_work < cap ? by_work : cap);
+  if (grid < floor_) grid = floor_;
   ratio_mask_kernel<T><<<grid, kThreads, 0, s>>>(ff, rf, n, th, eps, masks, mask_stride,
                                                  zero_counts);
   SFR_LAUNCH_STATUS();

@@ -83,9 +83,9 @@ select_hist0_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
     for (int u = 0; u < kHistUnroll; ++u) {
       const int64_t v = base + (int64_t)u * kHistThreads;
       const bool in = v < nvec;
-      x[u] = in ? ld_stream(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x[u] = in ? ld_once(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
       if constexpr (MODE != SFR_KEY_ABS)
-        y[u] = in ? ld_stream(b4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        y[u] = in ? ld_once(b4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
       else
         y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -186,9 +186,9 @@ select_hist1_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
     for (int u = 0; u < kFiltUnroll; ++u) {
       const int64_t v = base + (int64_t)u * kFiltThreads;
       const bool in = v < nvec;
-      x[u] = in ? ld_stream(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x[u] = in ? ld_once(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
       if constexpr (MODE != SFR_KEY_ABS)
-        y[u] = in ? ld_stream(b4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        y[u] = in ? ld_once(b4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
       else
         y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -358,8 +358,8 @@ __device__ __forceinline__ void load_chunk_keys(const float* __restrict__ a, con
 #pragma unroll
     for (int sl = 0; sl < kChunkVecs; ++sl) {
       const int64_t e0 = base + ((int64_t)sl * kApplyThreads + threadIdx.x) * 4;
-      x[sl] = ld_stream(reinterpret_cast<const float4*>(a + e0));
-      if constexpr (MODE != SFR_KEY_ABS) y[sl] = ld_stream(reinterpret_cast<const float4*>(b + e0));
+      x[sl] = ld_once(reinterpret_cast<const float4*>(a + e0));
+      if constexpr (MODE != SFR_KEY_ABS) y[sl] = ld_once(reinterpret_cast<const float4*>(b + e0));
       else y[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
@@ -509,9 +509,9 @@ select_apply_stream_kernel(const float* __restrict__ a, const float* __restrict_
     for (int u = 0; u < kApplyUnroll; ++u) {
       const int64_t v = base + (int64_t)u * kApplyThreads;
       const bool in = v < nvec;
-      x[u] = in ? ld_stream(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x[u] = in ? ld_once(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
       if constexpr (MODE != SFR_KEY_ABS)
-        y[u] = in ? ld_stream(b4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        y[u] = in ? ld_once(b4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
       else
         y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -523,7 +523,7 @@ select_apply_stream_kernel(const float* __restrict__ a, const float* __restrict_
       const uint32_t s1 = !none && key_from<MODE>(x[u].y, y[u].y, eps) >= thr;
       const uint32_t s2 = !none && key_from<MODE>(x[u].z, y[u].z, eps) >= thr;
       const uint32_t s3 = !none && key_from<MODE>(x[u].w, y[u].w, eps) >= thr;
-      __stcs(m4 + v, s0 | (s1 << 8) | (s2 << 16) | (s3 << 24));
+      m4[v] = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
     }
   }
   const int64_t tail0 = nvec << 2;
@@ -556,8 +556,8 @@ select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
 #pragma unroll
       for (int sl = 0; sl < kChunkVecs; ++sl) {
         const int64_t e0 = base + ((int64_t)sl * kApplyThreads + threadIdx.x) * 4;
-        x[sl] = ld_stream(reinterpret_cast<const float4*>(a + e0));
-        if constexpr (MODE != SFR_KEY_ABS) y[sl] = ld_stream(reinterpret_cast<const float4*>(b + e0));
+        x[sl] = ld_once(reinterpret_cast<const float4*>(a + e0));
+        if constexpr (MODE != SFR_KEY_ABS) y[sl] = ld_once(reinterpret_cast<const float4*>(b + e0));
         else y[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
@@ -567,7 +567,7 @@ select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
         const uint32_t s1 = key_from<MODE>(x[sl].y, y[sl].y, eps) > thr;
         const uint32_t s2 = key_from<MODE>(x[sl].z, y[sl].z, eps) > thr;
         const uint32_t s3 = key_from<MODE>(x[sl].w, y[sl].w, eps) > thr;
-        __stcs(reinterpret_cast<unsigned int*>(mask + e0), s0 | (s1 << 8) | (s2 << 16) | (s3 << 24));
+        *reinterpret_cast<unsigned int*>(mask + e0) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
       }
       continue;
     }
@@ -610,8 +610,7 @@ select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
         run += slab_total;  // every thread keeps the same running count
       }
       if (((valid >> (sl * 4)) & 0xfu) == 0xfu) {
-        __stcs(reinterpret_cast<unsigned int*>(mask + e0),
-               sel[0] | (sel[1] << 8) | (sel[2] << 16) | (sel[3] << 24));
+        *reinterpret_cast<unsigned int*>(mask + e0) = sel[0] | (sel[1] << 8) | (sel[2] << 16) | (sel[3] << 24);
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q)

@@ -49,8 +49,8 @@ masked_sumsq_kernel(const void* __restrict__ g, const uint8_t* __restrict__ mask
     for (int u = 0; u < kSumsqUnroll; ++u) {
       const int64_t v = base + (int64_t)u * kThreads;
       const bool in = v < nvec;
-      gg[u] = in ? load_g4<GT>(g, v) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if constexpr (MASK) mm[u] = in ? load_mask4(mask, v) : 0u;
+      gg[u] = in ? load_g4_once<GT>(g, v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (MASK) mm[u] = in ? load_mask4_once(mask, v) : 0u;
     }
     // fp32 partial over the 32 elements of this tile step, folded into a double per thread:
     // the rounding error of the norm stays ~1e-8 relative for any n.
@@ -172,10 +172,11 @@ __device__ __forceinline__ void update_one(float& p, float g, float& m, float& v
   s = ema_step<EMA>(p, s, c);
 }
 
-constexpr int kUpdCtasPerSm = 3;
+constexpr int kUpdThreads = 128;  // small CTAs, one 128-vector tile per CTA (tuned: tools/tune/tune_stream.cu)
+constexpr int kUpdCtasPerSm = 6;
 
 template <int OPT, int EMA, int GT>
-__global__ void __launch_bounds__(kThreads, kUpdCtasPerSm)
+__global__ void __launch_bounds__(kUpdThreads, kUpdCtasPerSm)
 fused_update_kernel(float* __restrict__ p, void* __restrict__ g, float* __restrict__ m,
                     float* __restrict__ v, const uint8_t* __restrict__ mask,
                     float* __restrict__ ema, void* __restrict__ p_bf16, int64_t n,
@@ -199,8 +200,8 @@ fused_update_kernel(float* __restrict__ p, void* __restrict__ g, float* __restri
   float4* e4 = reinterpret_cast<float4*>(ema);
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int64_t vec = (int64_t)blockIdx.x * kThreads + threadIdx.x; vec < nvec;
-       vec += (int64_t)gridDim.x * kThreads) {
+  for (int64_t vec = (int64_t)blockIdx.x * kUpdThreads + threadIdx.x; vec < nvec;
+       vec += (int64_t)gridDim.x * kUpdThreads) {
     // issue every load of this step before the first use: 4-6 independent 128-bit
     // requests in flight per thread
     const float4 gg = load_g4<GT>(g, vec);
@@ -226,7 +227,7 @@ fused_update_kernel(float* __restrict__ p, void* __restrict__ g, float* __restri
       uint2 packed;
       packed.x = *reinterpret_cast<uint32_t*>(&lo);
       packed.y = *reinterpret_cast<uint32_t*>(&hi);
-      __stcs(reinterpret_cast<uint2*>(p_bf16) + vec, packed);
+      *(reinterpret_cast<uint2*>(p_bf16) + vec) = packed;
     }
   }
 
@@ -349,9 +350,9 @@ void launch_update_gt(int gt, int grid, cudaStream_t s, float* p, void* g, float
                       const uint8_t* mask, float* ema, void* p_bf16, int64_t n,
                       const UpdateConsts& c, const UpdateConsts* c_dev, const double* clip_sumsq) {
   if (gt == SFR_F32)
-    fused_update_kernel<OPT, EMA, SFR_F32><<<grid, kThreads, 0, s>>>(p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq);
+    fused_update_kernel<OPT, EMA, SFR_F32><<<grid, kUpdThreads, 0, s>>>(p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq);
   else
-    fused_update_kernel<OPT, EMA, SFR_BF16><<<grid, kThreads, 0, s>>>(p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq);
+    fused_update_kernel<OPT, EMA, SFR_BF16><<<grid, kUpdThreads, 0, s>>>(p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq);
 }
 
 template <int OPT>
@@ -443,7 +444,7 @@ extern "C" int sfr_fused_update(float* p, void* g, float* m, float* v, const uin
   }
 
   const int64_t nvec = n >> 2;
-  const int grid = persistent_grid((nvec + kThreads - 1) / kThreads, kUpdCtasPerSm * 8);
+  const int grid = full_grid((nvec + kUpdThreads - 1) / kUpdThreads);
   switch (a->opt) {
     case SFR_OPT_SGD:
       launch_update_ema<SFR_OPT_SGD>(a->ema_mode, a->g_dtype, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq);
