@@ -234,10 +234,12 @@ typedef struct sfr_update_args {
   double clip_max_norm;/* used when clip_sumsq != NULL                    */
 } sfr_update_args;
 
-/* step_counter_dev / consts_scratch_dev: NULL for plain launches (args->step is used).  For launches
- * that will be REPLAYED (CUDA graphs) pass a device int64 counter and >= 128 bytes of 16-byte-aligned
- * device scratch: a one-thread kernel increments the counter and forms the step-dependent constants
- * (bias corrections, SGD first-step flag) on the device, so every replay advances the optimizer step. */
+/* consts_scratch_dev (optional, >= 128 bytes of 16-byte-aligned device memory): a one-thread prep kernel
+ * leaves the step-dependent scalars and the clip coefficient there, so the main kernel reads plain
+ * floats instead of deriving the coefficient from *clip_sumsq in front of every CTA (~3.5 % faster when
+ * clipping).  step_counter_dev (optional, requires the scratch): a device int64 that the prep kernel
+ * increments and uses INSTEAD of args->step — the optimizer step then lives on the device and advances
+ * at every replay of a captured launch (CUDA graphs).  Both NULL: everything by value, args->step. */
 #define SFR_UPDATE_CONSTS_BYTES 128
 SFR_API int sfr_fused_update(float* p, void* g, float* m, float* v, const uint8_t* mask,
                      float* ema, void* p_bf16, int64_t n,

@@ -144,6 +144,14 @@ __device__ __forceinline__ float clip_coef_from_sumsq(const double* sumsq, float
   return coef > 1.0f ? 1.0f : coef;  // keeps NaN, like torch.clamp(max=1.0)
 }
 
+// The same coefficient with one double sqrt per WARP instead of per thread (FP64 is the scarce pipe;
+// one-tile CTAs make a per-thread sqrt run ~1.7e8 times per launch).  Must be called by full warps.
+__device__ __forceinline__ float clip_coef_warp(const double* sumsq, float max_norm) {
+  float c = 0.f;
+  if ((threadIdx.x & 31) == 0) c = clip_coef_from_sumsq(sumsq, max_norm);
+  return __shfl_sync(kFullMask, c, 0);
+}
+
 // ---- reductions -----------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

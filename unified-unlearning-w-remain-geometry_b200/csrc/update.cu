@@ -105,6 +105,20 @@ struct UpdateConsts {
   int has_momentum;
 };
 
+// Step-dependent scalars that a one-thread prep kernel leaves in device scratch (when the caller
+// provides one): Adam's bias corrections from the DEVICE step counter (graph replay), SGD's
+// first-step flag, and the clip coefficient.  Everything the kernel needs to decide WHICH loads to
+// issue stays in the by-value UpdateConsts; these values are first used in the arithmetic, after the
+// data loads are in flight, so reading them never stalls the start of a CTA (a coefficient derived
+// in-kernel from *clip_sumsq does: load -> double sqrt -> divide in front of every short-lived CTA
+// costs ~3.5 %, measured).
+struct DevConsts {
+  float neg_step_size;
+  float bc2_sqrt;
+  float clip_coef;
+  uint32_t sgd_first_step;
+};
+
 // ---- slow / EMA weights ----------------------------------------------------------------
 // Returns the new slow value; may rewrite p (SLOWFAST).
 template <int EMA>
@@ -180,18 +194,27 @@ __global__ void __launch_bounds__(kUpdThreads, kUpdCtasPerSm)
 fused_update_kernel(float* __restrict__ p, void* __restrict__ g, float* __restrict__ m,
                     float* __restrict__ v, const uint8_t* __restrict__ mask,
                     float* __restrict__ ema, void* __restrict__ p_bf16, int64_t n,
-                    UpdateConsts c_arg, const UpdateConsts* __restrict__ c_dev,
+                    UpdateConsts c_arg, const DevConsts* __restrict__ c_dev,
                     const double* __restrict__ clip_sumsq) {
-  // Replay-safe launches (CUDA graphs) read the step-dependent constants from device memory, where
-  // update_consts_kernel formed them from a device-side step counter; plain launches get them by value.
-  const UpdateConsts c = c_dev ? *c_dev : c_arg;
+  UpdateConsts c = c_arg;
+  float coef_dev = 1.0f;
+  if (c_dev != nullptr) {
+    if constexpr (OPT == SFR_OPT_SGD) {
+      // only SGD's momentum-buffer init changes WHICH loads are issued (read_m below)
+      if (c_dev->sgd_first_step) c.flags |= SFR_F_SGD_FIRST_STEP; else c.flags &= ~SFR_F_SGD_FIRST_STEP;
+    } else {
+      c.neg_step_size = c_dev->neg_step_size;
+      c.bc2_sqrt = c_dev->bc2_sqrt;
+    }
+    coef_dev = c_dev->clip_coef;
+  }
   constexpr bool kHasV = OPT != SFR_OPT_SGD;
   constexpr bool kHasEma = EMA != SFR_EMA_NONE;
   const bool use_mask = (c.flags & (SFR_F_MASK | SFR_F_MASK_AFTER_CLIP)) != 0;
   const bool has_m = kHasV || c.has_momentum;
   const bool read_m = has_m && !(OPT == SFR_OPT_SGD && (c.flags & SFR_F_SGD_FIRST_STEP));
   // coef == 1.0f exactly when not clipping: g * 1.0f is an exact no-op
-  const float coef = clip_sumsq ? clip_coef_from_sumsq(clip_sumsq, c.max_norm) : 1.0f;
+  const float coef = clip_sumsq ? (c_dev ? coef_dev : clip_coef_warp(clip_sumsq, c.max_norm)) : 1.0f;
 
   const int64_t nvec = n >> 2;
   float4* p4 = reinterpret_cast<float4*>(p);
@@ -210,7 +233,6 @@ fused_update_kernel(float* __restrict__ p, void* __restrict__ g, float* __restri
     float4 mm = read_m ? ld_stream(m4 + vec) : zero4;
     float4 vv = kHasV ? ld_stream(v4 + vec) : zero4;
     float4 ee = kHasEma ? ld_stream(e4 + vec) : zero4;
-
     update_one<OPT, EMA>(pp.x, gg.x, mm.x, vv.x, ee.x, mask_byte_to_f32(mk, 0), coef, c);
     update_one<OPT, EMA>(pp.y, gg.y, mm.y, vv.y, ee.y, mask_byte_to_f32(mk, 1), coef, c);
     update_one<OPT, EMA>(pp.z, gg.z, mm.z, vv.z, ee.z, mask_byte_to_f32(mk, 2), coef, c);
@@ -335,20 +357,23 @@ __host__ __device__ inline UpdateConsts make_update_consts(const sfr_update_args
 }
 
 __global__ void update_consts_kernel(sfr_update_args a, bool has_momentum, long long* step_counter,
-                                     UpdateConsts* out) {
-  const long long step = ++(*step_counter);       // optimizer state['step'] lives on the device
-  UpdateConsts c = make_update_consts(a, step, has_momentum);
-  if (a.opt == SFR_OPT_SGD && has_momentum) {
-    // first use of the momentum buffer (buf = clone(grad)) is decided by the device counter too
-    if (step == 1) c.flags |= SFR_F_SGD_FIRST_STEP; else c.flags &= ~SFR_F_SGD_FIRST_STEP;
-  }
-  *out = c;
+                                     const double* clip_sumsq, DevConsts* out) {
+  // optimizer state['step'] lives on the device when a counter is given (graph replay)
+  const long long step = step_counter ? ++(*step_counter) : (long long)a.step;
+  const UpdateConsts c = make_update_consts(a, step, has_momentum);
+  DevConsts d;
+  d.neg_step_size = c.neg_step_size;
+  d.bc2_sqrt = c.bc2_sqrt;
+  d.clip_coef = clip_sumsq ? clip_coef_from_sumsq(clip_sumsq, (float)a.clip_max_norm) : 1.0f;
+  // first use of the momentum buffer (buf = clone(grad)): from the device counter if there is one
+  d.sgd_first_step = step_counter ? (step == 1) : ((a.flags & SFR_F_SGD_FIRST_STEP) != 0);
+  *out = d;
 }
 
 template <int OPT, int EMA>
 void launch_update_gt(int gt, int grid, cudaStream_t s, float* p, void* g, float* m, float* v,
                       const uint8_t* mask, float* ema, void* p_bf16, int64_t n,
-                      const UpdateConsts& c, const UpdateConsts* c_dev, const double* clip_sumsq) {
+                      const UpdateConsts& c, const DevConsts* c_dev, const double* clip_sumsq) {
   if (gt == SFR_F32)
     fused_update_kernel<OPT, EMA, SFR_F32><<<grid, kUpdThreads, 0, s>>>(p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq);
   else
@@ -358,7 +383,7 @@ void launch_update_gt(int gt, int grid, cudaStream_t s, float* p, void* g, float
 template <int OPT>
 void launch_update_ema(int ema_mode, int gt, int grid, cudaStream_t s, float* p, void* g,
                        float* m, float* v, const uint8_t* mask, float* ema, void* p_bf16,
-                       int64_t n, const UpdateConsts& c, const UpdateConsts* c_dev,
+                       int64_t n, const UpdateConsts& c, const DevConsts* c_dev,
                        const double* clip_sumsq) {
   switch (ema_mode) {
     case SFR_EMA_DDPM: launch_update_gt<OPT, SFR_EMA_DDPM>(gt, grid, s, p, g, m, v, mask, ema, p_bf16, n, c, c_dev, clip_sumsq); break;
@@ -432,15 +457,16 @@ extern "C" int sfr_fused_update(float* p, void* g, float* m, float* v, const uin
   if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
 
   UpdateConsts c = make_update_consts(*a, a->step, has_momentum);
-  const UpdateConsts* c_dev = nullptr;
+  const DevConsts* c_dev = nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (step_counter != nullptr) {
-    // graph-replayable: ++(*step_counter) on the device, constants formed there
-    SFR_REQUIRE_PTR(consts_scratch);
+  if (step_counter != nullptr) SFR_REQUIRE_PTR(consts_scratch);
+  if (consts_scratch != nullptr) {
+    // one-thread prep kernel: step-dependent scalars (from the device counter if given: graph
+    // replay) and the clip coefficient, precomputed so the main kernel never stalls on them
     if (!aligned16(consts_scratch)) return SFR_ERR_ALIGN;
-    update_consts_kernel<<<1, 1, 0, s>>>(*a, has_momentum, step_counter,
-                                         reinterpret_cast<UpdateConsts*>(consts_scratch));
-    c_dev = reinterpret_cast<const UpdateConsts*>(consts_scratch);
+    update_consts_kernel<<<1, 1, 0, s>>>(*a, has_momentum, step_counter, clip_sumsq,
+                                         reinterpret_cast<DevConsts*>(consts_scratch));
+    c_dev = reinterpret_cast<const DevConsts*>(consts_scratch);
   }
 
   const int64_t nvec = n >> 2;

@@ -65,7 +65,8 @@ class HotPath:
         self._select = None
         # replay-safe mode (CUDA graphs): the optimizer step counter lives on the device
         self.step_dev: Optional[torch.Tensor] = None
-        self._consts_dev: Optional[torch.Tensor] = None
+        # device scratch for the prep kernel of the fused update (step-dependent scalars, clip coefficient)
+        self._consts_dev: Optional[torch.Tensor] = torch.zeros(128, dtype=torch.uint8, device=self.device)
         # optional probe called with a label right after each kernel launch (bench.py records a
         # CUDA event there to attribute device time per kernel); None on the normal path
         self.trace = None
@@ -81,7 +82,6 @@ class HotPath:
         (nothing may be allocated during capture)."""
         if self.step_dev is None:
             self.step_dev = torch.full((1,), self.step_count, dtype=torch.int64, device=self.device)
-            self._consts_dev = torch.zeros(128, dtype=torch.uint8, device=self.device)
         sgd = self.opt.kind == "sgd"
         if not sgd or self.opt.momentum != 0.0:
             self.buffer("m")
@@ -287,7 +287,9 @@ class HotPath:
         capi.fused_update(p, g, None if (sgd and self.opt.momentum == 0.0) else self.m,
                           None if sgd else self.v, mask, self.slow if use_ema else None, a,
                           clip_sumsq=clip, p_bf16=p_bf16, step_counter=self.step_dev,
-                          consts_scratch=self._consts_dev)
+                          # the prep kernel pays off when there is a clip coefficient to precompute or a
+                          # device step counter to advance; otherwise everything goes by value
+                          consts_scratch=self._consts_dev if (clip is not None or self.step_dev is not None) else None)
         self._t("fused_update_ema" if use_ema else "fused_update")
 
     def forget_step(self, p: torch.Tensor, g: torch.Tensor, *, mask: Optional[torch.Tensor] = None,
