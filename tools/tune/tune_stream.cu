@@ -53,6 +53,36 @@ __global__ void __launch_bounds__(THREADS, CTAS) k3(float* __restrict__ p, const
   }
 }
 
+// read-only shape (clip norm / histogram passes): 1 stream read, register reduce
+template <int THREADS, int UNROLL, int CTAS, int H>
+__global__ void __launch_bounds__(THREADS, CTAS) kr(const float* __restrict__ g, int64_t nvec, unsigned* __restrict__ out) {
+  const float4* g4 = (const float4*)g; unsigned acc = 0;
+  const int64_t tile = (int64_t)THREADS * UNROLL, ntiles = (nvec + tile - 1) / tile;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * tile + threadIdx.x; float4 x[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) { int64_t v = base + (int64_t)u * THREADS; x[u] = v < nvec ? ld<H>(g4 + v) : make_float4(0, 0, 0, 0); }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) acc += (__float_as_uint(x[u].x) >> 16) ^ (__float_as_uint(x[u].y) >> 16) ^ (__float_as_uint(x[u].z) >> 16) ^ (__float_as_uint(x[u].w) >> 16);
+  }
+  if (acc == 0xdeadbeefu) out[0] = acc;
+}
+// apply shape: read 1 stream, write 1 byte per element
+template <int THREADS, int UNROLL, int CTAS, int H>
+__global__ void __launch_bounds__(THREADS, CTAS) ka(const float* __restrict__ g, unsigned* __restrict__ mask, int64_t nvec, unsigned thr) {
+  const float4* g4 = (const float4*)g;
+  const int64_t tile = (int64_t)THREADS * UNROLL, ntiles = (nvec + tile - 1) / tile;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * tile + threadIdx.x; float4 x[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) { int64_t v = base + (int64_t)u * THREADS; x[u] = v < nvec ? ld<H>(g4 + v) : make_float4(0, 0, 0, 0); }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) { int64_t v = base + (int64_t)u * THREADS; if (v < nvec) {
+      unsigned m = (__float_as_uint(x[u].x) > thr) | ((__float_as_uint(x[u].y) > thr) << 8) | ((__float_as_uint(x[u].z) > thr) << 16) | ((__float_as_uint(x[u].w) > thr) << 24);
+      mask[v] = m; } }
+  }
+}
+
 static float* dalloc(int64_t n) { float* p; cudaMalloc(&p, n * 4); cudaMemset(p, 0, n * 4); return p; }
 static char* flushbuf; 
 template <typename F> float timeit(F f) {
@@ -69,11 +99,15 @@ int main() {
     printf("k1 threads=%d unroll=%d ctas=%d hint=%d gridmult=%d  %.4f ms  %.1f GB/s\n", T, U, C, H, MULT, ms, 12.0 * n / ms / 1e6); }
 #define RUN3(T, U, C, H, MULT) { int64_t gg = (int64_t)sms * C * MULT, nt = (nvec + (int64_t)T * U - 1) / ((int64_t)T * U); int grid = (int)(gg < nt ? gg : nt); float ms = timeit([&] { k3<T, U, C, H><<<grid, T>>>(p, g, m, v, e, nvec); }); \
     printf("k3 threads=%d unroll=%d ctas=%d hint=%d gridmult=%d  %.4f ms  %.1f GB/s\n", T, U, C, H, MULT, ms, 36.0 * n / ms / 1e6); }
-  RUN1(256, 2, 8, PLAIN, 8) RUN1(256, 2, 8, PLAIN, 16) RUN1(256, 2, 8, PLAIN, 32) RUN1(256, 2, 8, PLAIN, 64) RUN1(256, 2, 8, PLAIN, 128)
-  RUN1(128, 2, 16, PLAIN, 16) RUN1(128, 2, 16, PLAIN, 32) RUN1(128, 2, 16, PLAIN, 64) RUN1(128, 4, 8, PLAIN, 32) RUN1(256, 4, 4, PLAIN, 32) RUN1(256, 4, 4, PLAIN, 64)
-  RUN1(128, 1, 16, PLAIN, 32) RUN1(128, 1, 16, PLAIN, 64) RUN1(64, 2, 32, PLAIN, 32) RUN1(64, 4, 16, PLAIN, 32)
-  RUN3(128, 1, 8, PLAIN, 32) RUN3(128, 1, 8, PLAIN, 128) RUN3(128, 1, 8, PLAIN, 512) RUN3(128, 1, 8, PLAIN, 100000) RUN3(64, 1, 16, PLAIN, 100000)
-  RUN3(128, 1, 6, PLAIN, 100000) RUN3(128, 1, 10, PLAIN, 100000) RUN3(96, 1, 10, PLAIN, 100000) RUN3(192, 1, 5, PLAIN, 100000)
+  unsigned* outp; cudaMalloc(&outp, 64);
+#define RUNR(T, U, C, H, MULT) { int64_t gg = (int64_t)sms * C * MULT, nt = (nvec + (int64_t)T * U - 1) / ((int64_t)T * U); int grid = (int)(gg < nt ? gg : nt); float ms = timeit([&] { kr<T, U, C, H><<<grid, T>>>(g, nvec, outp); }); \
+    printf("kr threads=%d unroll=%d ctas=%d hint=%d gridmult=%d  %.4f ms  %.1f GB/s\n", T, U, C, H, MULT, ms, 4.0 * n / ms / 1e6); }
+#define RUNA(T, U, C, H, MULT) { int64_t gg = (int64_t)sms * C * MULT, nt = (nvec + (int64_t)T * U - 1) / ((int64_t)T * U); int grid = (int)(gg < nt ? gg : nt); float ms = timeit([&] { ka<T, U, C, H><<<grid, T>>>(g, (unsigned*)m, nvec, 0x3c000000u); }); \
+    printf("ka threads=%d unroll=%d ctas=%d hint=%d gridmult=%d  %.4f ms  %.1f GB/s\n", T, U, C, H, MULT, ms, 5.0 * n / ms / 1e6); }
+  RUNR(256, 8, 4, CS, 1) RUNR(256, 8, 4, PLAIN, 1) RUNR(256, 4, 8, CS, 1) RUNR(256, 4, 8, CS, 8) RUNR(256, 4, 8, CS, 32) RUNR(128, 4, 16, CS, 32)
+  RUNR(128, 2, 16, CS, 32) RUNR(128, 8, 8, CS, 32) RUNR(256, 4, 8, NC, 32) RUNR(256, 4, 8, PLAIN, 32) RUNR(1024, 4, 1, CS, 1) RUNR(1024, 4, 2, CS, 1) RUNR(128, 4, 16, CS, 100000) RUNR(256, 8, 4, CS, 32)
+  RUNA(256, 4, 4, CS, 1) RUNA(256, 4, 4, PLAIN, 1) RUNA(256, 8, 4, CS, 2) RUNA(128, 2, 16, CS, 32) RUNA(128, 2, 16, PLAIN, 32) RUNA(128, 4, 16, CS, 32)
+  RUNA(128, 4, 16, PLAIN, 32) RUNA(256, 4, 8, CS, 32) RUNA(128, 2, 16, CS, 100000) RUNA(128, 4, 8, CS, 100000) RUNA(256, 8, 4, CS, 32) RUNA(128, 8, 8, CS, 32)
   // torch-style copy for reference (read + write)
   { float ms = timeit([&] { cudaMemcpyAsync(p, g, n * 4, cudaMemcpyDeviceToDevice); }); printf("memcpy d2d %.4f ms %.1f GB/s (read+write)\n", ms, 8.0 * n / ms / 1e6); }
   return 0;

@@ -28,8 +28,9 @@ namespace {
 constexpr int kThreads = 256;
 
 // ------------------------------------------------------------------ masked sum of squares
-constexpr int kSumsqCtasPerSm = 4;
-constexpr int kSumsqUnroll = 8;
+constexpr int kSumsqCtasPerSm = 8;
+constexpr int kSumsqUnroll = 4;
+constexpr int kSumsqGridWaves = 16;  // SMs x 8 x 16 CTAs, one double atomic each (tuned: tools/tune)
 
 template <int GT, bool MASK>
 __global__ void __launch_bounds__(kThreads, kSumsqCtasPerSm)
@@ -409,7 +410,7 @@ extern "C" int sfr_masked_sumsq(const void* g, int g_dtype, const uint8_t* mask,
   if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
   const int64_t nvec = n >> 2;
   const int64_t tile = (int64_t)kThreads * kSumsqUnroll;
-  const int grid = persistent_grid((nvec + tile - 1) / tile, kSumsqCtasPerSm);
+  const int grid = persistent_grid((nvec + tile - 1) / tile, kSumsqCtasPerSm * kSumsqGridWaves);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (g_dtype == SFR_F32) {
     if (mask) masked_sumsq_kernel<SFR_F32, true><<<grid, kThreads, 0, s>>>(g, mask, n, out);
