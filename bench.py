@@ -376,12 +376,13 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the K2b select timing outside the step")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel (default: the committed ncu capture "
-                         "profiles/r1_ncu_full_fused_update_n675M_raw.csv when --elems is the default)")
+                         "profiles/r1_ncu_full_step_kernels_n675M_raw.csv when --elems is the default)")
     args = ap.parse_args()
     if args.traffic is None and args.elems == N3:
-        # ncu --set full, fused_update_kernel<AdamW,EMA_DIT,f32> at n = N3: dram__bytes_read.sum 13.502762 GB
-        # + dram__bytes_write.sum 10.747480 GB per launch (algorithmic: 36 B x N3 = 24.305 GB)
-        args.traffic = 13.502762e9 + 10.747480e9
+        # ncu --set full (profiles/r1_ncu_full_step_kernels_n675M_raw.csv), fused_update_kernel<AdamW,EMA_DIT,f32>
+        # at n = N3: dram__bytes_read.sum 13.502611 GB + dram__bytes_write.sum 10.745242 GB per launch
+        # (algorithmic: 36 B x N3 = 24.305 GB)
+        args.traffic = 13.502611e9 + 10.745242e9
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                  # timing rule: W >= 3
     world = int(os.environ.get("WORLD_SIZE", "1"))
