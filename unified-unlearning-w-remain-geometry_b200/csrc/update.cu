@@ -299,7 +299,7 @@ ema_only_kernel(const float* __restrict__ p, float* __restrict__ ema, int64_t n,
   }
 }
 
-void fill_ema_consts(UpdateConsts& c, int ema_mode, double a) {
+__host__ __device__ inline void fill_ema_consts(UpdateConsts& c, int ema_mode, double a) {
   // Python computes (1 - a) in double; torch rounds each scalar to fp32 when the op runs.
   if (ema_mode == SFR_EMA_DDPM) {         // (1.0 - mu) * p + mu * s
     c.ema_c1 = (float)(1.0 - a);
@@ -343,17 +343,7 @@ __host__ __device__ inline UpdateConsts make_update_consts(const sfr_update_args
     c.eps = (float)a.eps;
     c.decay_mul = (float)(1.0 - a.lr * a.weight_decay);
   }
-  // Python computes (1 - a) in double; torch rounds each scalar to fp32 when the op runs.
-  if (a.ema_mode == SFR_EMA_DDPM) {             // (1.0 - mu) * p + mu * s
-    c.ema_c1 = (float)(1.0 - a.ema_a);
-    c.ema_c2 = (float)a.ema_a;
-  } else if (a.ema_mode == SFR_EMA_DIT) {       // s.mul_(d).add_(p, alpha=1 - d)
-    c.ema_c1 = (float)a.ema_a;
-    c.ema_c2 = (float)(1.0 - a.ema_a);
-  } else if (a.ema_mode == SFR_EMA_SLOWFAST) {  // (1 - b) * prev + b * p
-    c.ema_c1 = (float)(1.0 - a.ema_a);
-    c.ema_c2 = (float)a.ema_a;
-  }
+  fill_ema_consts(c, a.ema_mode, a.ema_a);
   return c;
 }
 

@@ -16,7 +16,7 @@ single torch optimizer object of every reference loop.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, Optional, Sequence
 
 import torch

@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import os
 import pickle
-from typing import Dict, Iterable, List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import torch
 

@@ -8,8 +8,7 @@ forward by the flat-vector kernels.
 from __future__ import annotations
 
 import math
-import os
-from typing import Callable, Dict, Iterable, Optional, Sequence
+from typing import Dict, Optional
 
 import torch
 

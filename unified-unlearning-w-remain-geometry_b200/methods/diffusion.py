@@ -13,7 +13,6 @@ model plus closures that produce the (already alpha-weighted) losses:
 from __future__ import annotations
 
 import os
-import pickle
 from dataclasses import dataclass
 from typing import Callable, Dict, Iterable, Optional
 
@@ -75,7 +74,7 @@ def per_sample_grad_rows(model: torch.nn.Module, per_sample_loss: Callable, batc
     per_sample_loss(params_and_buffers: dict, *sample) -> scalar loss of ONE sample, written with
     torch.func.functional_call.  Rows follow the flat layout (trainable parameters, named_parameters order).
     """
-    from torch.func import functional_call, grad, vmap  # noqa: F401  (functional_call is for the caller)
+    from torch.func import grad, vmap
     params = {n: p.detach() for n, p in model.named_parameters() if p.requires_grad}
     frozen = {n: p.detach() for n, p in model.named_parameters() if not p.requires_grad}
     buffers = {n: b for n, b in model.named_buffers()}
