@@ -589,3 +589,58 @@ def test_no_out_of_bounds_writes(sfr, dev, n):
     for name, (buf, view, guard) in bufs.items():
         assert _guards_intact(buf, n, guard, S), f"{name}: write outside [0, n)"
     assert _guards_intact(mb, n, mg, 77) and _guards_intact(tb, n, tg, 77) and _guards_intact(pb, n, pg, 3.0)
+
+
+# =============================================================================== property tests (hypothesis)
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(data=st.data())
+def test_k2b_property_random_distributions(sfr, dev, data):
+    """Exact top-k over random sizes / value distributions / k: bit-exact against the stable-argsort oracle."""
+    n = data.draw(st.integers(1, 60_000))
+    seed = data.draw(st.integers(0, 2 ** 31 - 1))
+    kind = data.draw(st.sampled_from(["gauss", "lognormal", "quantized", "sparse", "denormal", "mixed_special"]))
+    g = gen(seed)
+    if kind == "gauss":
+        x = torch.randn(n, generator=g) * 10 ** data.draw(st.integers(-20, 10))
+    elif kind == "lognormal":
+        x = torch.exp(torch.randn(n, generator=g) * 8) * torch.where(torch.rand(n, generator=g) < 0.5, -1.0, 1.0)
+    elif kind == "quantized":
+        x = torch.randint(-5, 6, (n,), generator=g).float() * 0.5
+    elif kind == "sparse":
+        x = torch.randn(n, generator=g) * (torch.rand(n, generator=g) < 0.05)
+    elif kind == "denormal":
+        x = torch.randn(n, generator=g) * 1e-41
+    else:
+        x = torch.randn(n, generator=g)
+        idx = torch.randint(0, n, (max(1, n // 50),), generator=g)
+        x[idx] = torch.tensor([float("inf"), float("-inf"), float("nan"), 0.0, -0.0])[torch.randint(0, 5, idx.shape, generator=g)]
+    n_num = int((~x.isnan()).sum())
+    k = data.draw(st.integers(0, n_num))              # NaN never ranks ahead of a number
+    mask, _ = run_topk(sfr, dev, x, k)
+    assert torch.equal(mask, O.topk_mask_flat(x, k))
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(1, 40_000), seed=st.integers(0, 2 ** 31 - 1), rows=st.integers(1, 4),
+       divisor=st.sampled_from([1.0, 3.0, 50.0, 2000.0]))
+def test_k1_k2a_property_bit_exact(sfr, dev, n, seed, rows, divisor):
+    g = gen(seed)
+    n_pad = (n + 7) // 8 * 8
+    gr = torch.randn(rows, n_pad, generator=g)[:, :n] * 10 ** float(torch.randint(-8, 3, (1,), generator=g))
+    acc0 = torch.rand(n, generator=g) * 1e-6
+    ref = acc0.clone()
+    for r in gr:
+        O.flat_fisher_accum(ref, r, divisor)
+    acc = acc0.to(dev)
+    full = torch.zeros(rows, n_pad, device=dev)
+    full[:, :n] = gr.to(dev)
+    sfr.capi.fisher_accum(acc, full[:, :n] if rows > 1 else full[0, :n].clone(), divisor)
+    assert bits_equal(acc.cpu(), ref)
+    rf = torch.rand(n, generator=g) * 1e-6
+    th = float(torch.rand(1, generator=g) * 3)
+    mask = torch.empty(n, dtype=torch.uint8, device=dev)
+    sfr.capi.ratio_mask(acc, rf.to(dev), th, mask)
+    assert torch.equal(mask.cpu().bool(), O.flat_ratio_mask(ref, rf, th))
