@@ -114,7 +114,8 @@ select_hist0_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
 
 // ---- scratch layout (unsigned long long words) ------------------------------------------------
 //   [0, nchunks)                  per-chunk count of threshold-equal keys
-//   [nchunks, 2*nchunks)          exclusive scan of those counts (+ tie_base)
+//   [nchunks, 2*nchunks)          per scan block (kScanBlock chunks): exclusive tie base (+ tie_base);
+//                                 only the first ceil(nchunks / kScanBlock) words are used
 //   header (kCandHeader words):   [0] overflow flag, [1] number of regions, [2] region capacity,
 //                                 [8 + r] entries staged in region r
 //   candidate regions             cand_cap words: (flat index << 16) | key[15:0]
@@ -136,7 +137,7 @@ __host__ __device__ inline int64_t scratch_cand_cap(int64_t n) {
 // from this short list instead of re-reading the whole vector; if any region overflows (degenerate
 // inputs: most keys equal) a flag makes the apply fall back to the streaming count.
 constexpr int kFiltThreads = 256;
-constexpr int kFiltCtasPerSm = 4;
+constexpr int kFiltCtasPerSm = 6;
 constexpr int kFiltUnroll = 4;
 
 struct CandStage {
@@ -332,8 +333,8 @@ select_scan_kernel(int pass, sfr_select_state* __restrict__ state,
 // threshold than the budget allows (the COMMON case at scale: 675 M Gaussian values have ~20
 // elements per distinct fp32 value near the median), the lowest flat indices win, which needs the
 // number of threshold-equal keys in all earlier chunks:
-//   tie_count : scratch[c]            = #ties in chunk c            (streaming read, 4 B/elem)
-//   tie_scan  : scratch[nchunks + c]  = tie_base + #ties before c   (one CTA)
+//   tie_count : scratch[c]            = #ties in chunk c   (from the staged candidates; streaming fallback)
+//   tie scan  : two-level, see select_tie_block_sum_kernel
 //   apply     : chunks without ties stream (mask = key > thr); only chunks that contain a
 //               tie pay for the block-wide ordered ranking.
 constexpr int kApplyThreads = 256;
@@ -430,29 +431,44 @@ select_tie_count_candidates_kernel(int64_t n, const sfr_select_state* __restrict
   }
 }
 
-// Exclusive scan of the per-chunk tie counts by ONE CTA: 16 consecutive counters per thread,
-// warp-shuffle scan of the per-thread sums, 32 warp totals through shared memory — two barriers per
-// 16384 counters (82 k chunks at DiT-XL/2 size = 6 iterations).
-constexpr int kScanItems = 16;
+// Two-level exclusive scan of the per-chunk tie counts (a single-CTA scan of 82 k counters cost 96 us):
+//   tie_block_sum : one CTA per kScanBlock consecutive chunks -> scratch[nchunks + b] = their tie total
+//   tie_block_scan: one CTA turns the <= a few hundred block totals into exclusive bases (+ tie_base)
+// The prefix INSIDE a block is formed on demand by the apply kernel, and only by the CTAs whose chunk
+// contains a tie (a handful, except on degenerate inputs).
+constexpr int kScanBlock = 4096;  // chunks per scan block (= 33.5 M elements)
+
+__global__ void __launch_bounds__(256, 8)
+select_tie_block_sum_kernel(int64_t nchunks, const sfr_select_state* __restrict__ state,
+                            unsigned long long* __restrict__ scratch) {
+  if (!ties_need_order(state)) return;
+  __shared__ unsigned long long red[32];
+  const int64_t nblocks = (nchunks + kScanBlock - 1) / kScanBlock;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int64_t lo = blk * kScanBlock;
+    const int64_t hi = lo + kScanBlock < nchunks ? lo + kScanBlock : nchunks;
+    unsigned long long sum = 0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) sum += scratch[i];
+    sum = block_sum<unsigned long long>(sum, red);
+    if (threadIdx.x == 0) scratch[nchunks + blk] = sum;
+    __syncthreads();
+  }
+}
 
 __global__ void __launch_bounds__(1024, 1)
-select_tie_scan_kernel(int64_t nchunks, const sfr_select_state* __restrict__ state,
-                       const unsigned long long* __restrict__ tie_base,
-                       unsigned long long* __restrict__ scratch) {
+select_tie_block_scan_kernel(int64_t nchunks, const sfr_select_state* __restrict__ state,
+                             const unsigned long long* __restrict__ tie_base,
+                             unsigned long long* __restrict__ scratch) {
   if (!ties_need_order(state)) return;
   __shared__ unsigned long long warp_tot[32];
   __shared__ unsigned long long carry_s;
+  const int64_t nblocks = (nchunks + kScanBlock - 1) / kScanBlock;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long carry = tie_base ? *tie_base : 0ull;
-  const int64_t tile = (int64_t)1024 * kScanItems;
-  for (int64_t base = 0; base < nchunks; base += tile) {
-    const int64_t i0 = base + (int64_t)threadIdx.x * kScanItems;
-    unsigned long long v[kScanItems], mine = 0;
-#pragma unroll
-    for (int j = 0; j < kScanItems; ++j) {
-      v[j] = i0 + j < nchunks ? scratch[i0 + j] : 0ull;
-      mine += v[j];
-    }
+  unsigned long long* sums = scratch + nchunks;
+  for (int64_t base = 0; base < nblocks; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const unsigned long long mine = i < nblocks ? sums[i] : 0ull;
     unsigned long long incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -468,18 +484,13 @@ select_tie_scan_kernel(int64_t nchunks, const sfr_select_state* __restrict__ sta
         const unsigned long long up = __shfl_up_sync(kFullMask, wi, o);
         if (lane >= o) wi += up;
       }
-      warp_tot[lane] = wi - w;              // exclusive prefix of the warp totals
-      if (lane == 31) carry_s = wi;          // tile total
+      warp_tot[lane] = wi - w;
+      if (lane == 31) carry_s = wi;
     }
     __syncthreads();
-    unsigned long long run = carry + warp_tot[warp] + (incl - mine);
-#pragma unroll
-    for (int j = 0; j < kScanItems; ++j) {
-      if (i0 + j < nchunks) scratch[nchunks + i0 + j] = run;
-      run += v[j];
-    }
+    if (i < nblocks) sums[i] = carry + warp_tot[warp] + (incl - mine);  // exclusive base of block i
     carry += carry_s;
-    __syncthreads();                         // warp_tot / carry_s reused by the next tile
+    __syncthreads();
   }
 }
 
@@ -549,7 +560,6 @@ select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
   for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const int64_t base = c * kChunk;
     const unsigned long long chunk_ties = scratch[c];        // uniform over the CTA
-    unsigned long long run = scratch[nchunks + c];           // ties before this chunk
     if (chunk_ties == 0 && base + kChunk <= n) {
       // tie-free full chunk (almost all of them): straight-line stream, mask = key > thr
       float4 x[kChunkVecs], y[kChunkVecs];
@@ -571,6 +581,18 @@ select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
       }
       continue;
     }
+    // ties before this chunk = base of its scan block + counts of the earlier chunks of the block
+    __shared__ unsigned long long red64[32];
+    __shared__ unsigned long long run_s;
+    {
+      const int64_t blk = c / kScanBlock;
+      unsigned long long part = 0;
+      for (int64_t i = blk * kScanBlock + threadIdx.x; i < c; i += kApplyThreads) part += scratch[i];
+      part = block_sum<unsigned long long>(part, red64);
+      if (threadIdx.x == 0) run_s = scratch[nchunks + blk] + part;
+      __syncthreads();
+    }
+    unsigned long long run = run_s;
     uint32_t key[kChunkVecs][4], valid;
     load_chunk_keys<MODE>(a, b, eps, n, base, key, valid);
 #pragma unroll
@@ -727,6 +749,7 @@ extern "C" int sfr_select_apply(const float* a, const float* b, int key_mode, fl
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t nchunks = (n + kChunk - 1) / kChunk;
   const int grid = persistent_grid(nchunks, 8);
+  const int sum_grid = persistent_grid((nchunks + kScanBlock - 1) / kScanBlock, 8);
   const int64_t stile = (int64_t)kApplyThreads * kApplyUnroll;
   const int sgrid = persistent_grid(((n >> 2) + stile - 1) / stile, 4);
   // the per-chunk counters are accumulated into: clear them here so that apply is idempotent
@@ -735,7 +758,8 @@ extern "C" int sfr_select_apply(const float* a, const float* b, int key_mode, fl
 #define SFR_APPLY(M)                                                                                     \
   do {                                                                                                   \
     select_tie_count_kernel<M><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch);             \
-    select_tie_scan_kernel<<<1, 1024, 0, s>>>(nchunks, state, tie_base, scratch);                        \
+    select_tie_block_sum_kernel<<<sum_grid, 256, 0, s>>>(nchunks, state, scratch);                       \
+    select_tie_block_scan_kernel<<<1, 1024, 0, s>>>(nchunks, state, tie_base, scratch);                  \
     select_apply_kernel<M><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch, mask);           \
     select_apply_stream_kernel<M><<<sgrid, kApplyThreads, 0, s>>>(a, b, eps, n, state, mask);            \
   } while (0)
