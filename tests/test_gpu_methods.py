@@ -269,3 +269,31 @@ def test_per_sample_fim_vmap_producer_matches_retain_graph_loop(dev):
     l = torch.tensor([0.5, 1.0, 2.0], device=dev)
     w = adaptive_loss(l, 3, gamma=1.0, eps=1e-8, keepdim=True) / l
     assert torch.allclose(w.sum(), torch.tensor(3.0, device=dev)) and w[0] > w[1] > w[2]
+
+
+def test_host_gradient_feeder_pipeline(dev):
+    """Host-buffer entry of the path: pinned host gradients -> device, double-buffered; every step must see
+    exactly the gradients submitted for it, in order, and refuse pageable memory or an over-full pipe."""
+    import sfron_b200 as sfr
+    n = 100_003
+    feeder = sfr.HostGradientFeeder(n, dev, slots=("forget", "remain"))
+    hp = sfr.HotPath(n, dev, sfr.OptConfig())
+    host = [(torch.full((n,), float(i)).pin_memory(), torch.full((n,), float(-i)).pin_memory()) for i in range(5)]
+    feeder.submit(forget=host[0][0], remain=host[0][1])
+    want = torch.zeros(n)
+    for i in range(5):
+        g = feeder.acquire()
+        if i + 1 < 5:
+            feeder.submit(forget=host[i + 1][0], remain=host[i + 1][1])      # overlaps this step's kernels
+        assert float(g["forget"][0]) == float(i) and float(g["remain"][-1]) == float(-i)
+        hp.fisher_accumulate("forget", g["forget"], 1.0)
+        feeder.release()
+        want += float(i) ** 2
+    assert torch.equal(hp.forget_fisher.cpu(), want)
+    assert feeder.bytes_per_step == 2 * 4 * n
+    with pytest.raises(ValueError):
+        feeder.submit(forget=torch.zeros(n), remain=host[0][1])              # pageable host memory
+    feeder.submit(forget=host[0][0], remain=host[0][1])
+    feeder.submit(forget=host[1][0], remain=host[1][1])
+    with pytest.raises(RuntimeError):
+        feeder.submit(forget=host[2][0], remain=host[2][1])                  # depth 2: pipe is full
