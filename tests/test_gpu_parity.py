@@ -644,3 +644,65 @@ def test_k1_k2a_property_bit_exact(sfr, dev, n, seed, rows, divisor):
     mask = torch.empty(n, dtype=torch.uint8, device=dev)
     sfr.capi.ratio_mask(acc, rf.to(dev), th, mask)
     assert torch.equal(mask.cpu().bool(), O.flat_ratio_mask(ref, rf, th))
+
+
+# =============================================================================== full-size properties
+N3_FULL = 675_129_632          # DiT-XL/2 (BASELINE.json config 3): no CPU oracle at this size, exact identities instead
+
+
+def test_full_size_dit_properties(sfr, dev):
+    capi = sfr.capi
+    n = N3_FULL
+    gd = torch.Generator(device=dev).manual_seed(0)
+    g = torch.empty(n, device=dev).normal_(0, 1e-2, generator=gd)
+    # K1: two accumulations with divisor 2 give g*g exactly (x/2 is exact; x/2 + x/2 = x)
+    acc = torch.zeros(n, device=dev)
+    capi.fisher_accum(acc, g, 2.0)
+    capi.fisher_accum(acc, g, 2.0)
+    assert torch.equal(acc, g * g)
+    # K2a: equal Fishers -> ratio exactly 1 -> every element kept at th = 1, none at th just above 1;
+    # zero count + ones == n (checksum of checksums)
+    hp = sfr.HotPath(n, dev, sfr.OptConfig(kind="sgd", lr=0.0, momentum=0.9, weight_decay=0.0))
+    hp.set_buffer("forget_fisher", acc)
+    hp.set_buffer("remain_fisher", acc)
+    mask = hp.ratio_mask(1.0)
+    assert int(hp.zero_count[0]) == 0 and int(mask.sum(dtype=torch.int64)) == n
+    mask = hp.ratio_mask(1.0000001)
+    assert int(hp.zero_count[0]) == n and int(mask.sum(dtype=torch.int64)) == 0
+    hp.set_buffer("remain_fisher", torch.full((n,), 1e-4, device=dev))
+    mask = hp.ratio_mask(1.0)
+    ones = int(mask.sum(dtype=torch.int64))
+    assert int(hp.zero_count[0]) + ones == n and 0 < ones < n
+    assert torch.equal(mask.bool(), (acc + 1e-15) >= (torch.full_like(acc, 1e-4) + 1e-15))   # (a/b >= 1) == (a >= b), b > 0
+    # clip norm: masked + complement-masked sums of squares add up to the unmasked one
+    s_all, s_m, s_c = (torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(3))
+    capi.masked_sumsq(g, None, s_all)
+    capi.masked_sumsq(g, mask, s_m)
+    capi.masked_sumsq(g, 1 - mask, s_c)
+    assert abs((s_m + s_c - s_all).item()) <= 1e-9 * s_all.item()
+    # K3: a step with lr = 0 leaves the weights bit-identical and builds the momentum buffer = g * mask
+    p = torch.empty(n, device=dev).normal_(0, 0.02, generator=gd)
+    p0 = p.clone()
+    hp.set_buffer("mask", mask)
+    hp.forget_step(p, g, lr=0.0)
+    assert torch.equal(p, p0) and torch.equal(hp.m, g * mask)
+    del p0, acc
+    # K2b: exact count, ordering property, idempotence
+    k = n // 5
+    sel = hp.topk_mask(g, k, out=torch.empty(n, dtype=torch.uint8, device=dev)).bool()
+    assert int(sel.sum(dtype=torch.int64)) == k
+    a = g.abs()
+    assert a[sel].min() >= a[~sel].max()
+    st = hp.select_state()
+    assert st.count_gt + st.tie_budget == k and st.tie_budget <= st.count_eq
+
+
+def test_indexing_past_2_pow_31_and_degenerate_selects():
+    """n = 2^31 + 4099 elements through every kernel, and all-zero / 99.96 %-zero / two-valued selects at N3
+    (tools/stress.py; ~60 GB of device memory, ~20 s)."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress.py")], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"ok": true' in r.stdout
