@@ -138,6 +138,10 @@ class ShardGroup:
                     dist.broadcast(s, src=dist.get_global_rank(self.group, r) if self.group else r, group=self.group)
 
 
+# byte offset of sfr_select_state.thr_key: 5 x u64 (k, k_in_bin, count_gt, count_eq, tie_budget) + u32 prefix
+_THR_KEY_I32_INDEX = capi.SelectState.thr_key.offset // 4
+
+
 class ShardedHotPath(HotPath):
     """HotPath over this rank's shard, with the cross-rank reductions filled in."""
 
@@ -158,15 +162,14 @@ class ShardedHotPath(HotPath):
         return bins.clone()
 
     def tie_base_(self, state: torch.Tensor, local_bins: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
-        # number of threshold-equal keys on lower ranks: all-gather one count per rank
-        st = capi.read_select_state(state)
-        if st.select_all or st.select_none:
-            return None
-        mine = local_bins[st.thr_key & 0xFFFF].reshape(1).clone()
-        gathered = [torch.zeros_like(mine) for _ in range(self.shards.world)]
-        dist.all_gather(gathered, mine, group=self.shards.group)
-        base = tie_bases([int(x) for x in gathered])[self.shards.rank]
-        return torch.tensor([base], dtype=torch.int64, device=self.device)
+        """Number of threshold-equal keys on lower ranks, entirely on the device (no host read of the select
+        state): the threshold key sits at a fixed offset of the device struct (sfr_select_state.thr_key)."""
+        thr_key = state.view(torch.int32)[_THR_KEY_I32_INDEX].to(torch.int64) & 0xFFFFFFFF
+        mine = local_bins.index_select(0, (thr_key & 0xFFFF).reshape(1))          # local #keys == threshold
+        gathered = torch.empty(self.shards.world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(gathered, mine, group=self.shards.group)
+        # (for select_all / select_none the value is unused: the apply kernels do not order ties then)
+        return gathered[:self.shards.rank].sum().reshape(1)
 
     def ratio_mask(self, threshold: float, **kw) -> torch.Tensor:
         mask = super().ratio_mask(threshold, **kw)
