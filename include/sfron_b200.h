@@ -165,8 +165,9 @@ SFR_API int sfr_select_hist(const float* a, const float* b, int key_mode, float 
 SFR_API int sfr_select_scan(int pass, sfr_select_state* state_dev,
                     unsigned long long* bins_dev, sfr_stream_t stream);
 /* tie_base_dev: device u64 (NULL = 0).  scratch_dev: the SAME device u64 array of at least
- * sfr_select_scratch_elems(n) elements that pass 1 filled (per-chunk tie counts, their scan, and
- * the staged candidates; read only when ties must be ordered). */
+ * sfr_select_scratch_elems(n) elements that pass 1 filled (per-chunk tie counts, per-block tie
+ * bases, and the staged candidates; read only when ties must be ordered).  sfr_select_apply may be
+ * repeated after one pass 1 (it re-derives the tie counts each time). */
 SFR_API int64_t sfr_select_scratch_elems(int64_t n);
 SFR_API int sfr_select_apply(const float* a, const float* b, int key_mode, float eps,
                      int64_t n, const sfr_select_state* state_dev,
