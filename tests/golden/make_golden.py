@@ -11,6 +11,10 @@ What is executed from the reference, unmodified:
   * DDPM/generate_fisher_mask.py, SD/train-scripts/generate_fisher_mask.py        (as subprocesses)
   * DiT/generate_mask.py main()
   * DDPM/models/ema.py EMAHelper, DDPM/functions/__init__.py get_optimizer
+  * DDPM/runners/diffusion.py  Diffusion.generate_fisher / generate_mask / sfron_forget /
+    saliency_unlearn, whole methods, with three shims: a 411-parameter network of the same call
+    interface in place of Conditional_Model, synthetic loaders in place of get_forget_dataset,
+    and sample_visualization (the 1000-step sampler after a snapshot) stubbed out
   * DiT/forget.py update_ema / cosine_lr_scheduler (function bodies extracted with `ast`,
     because the module imports diffusers at top level, absent here)
 The forget-loop bodies of DDPM/runners/diffusion.py:1122-1180 and DiT/forget.py:285-322 are
@@ -307,6 +311,182 @@ def ddpm_loop():
     print("wrote ddpm loop")
 
 
+# ------------------------------------------------------------------- DDPM runner, executed whole
+class TinyCond(nn.Module):
+    """411-parameter stand-in for DDPM/models/diffusion.py:Conditional_Model with the same call
+    interface (`model(x, t, c, mode="train"|"test", cond_drop_prob=, cond_scale=)`, classifier-free
+    guidance with a `null_classes_emb`, :329-366).  Only the network is substituted (the full-size
+    U-Net needs ch=128 => >= 3 M parameters per recorded gradient); every line of the runner methods
+    below is the reference's."""
+    instances = []
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.conv_in = nn.Conv2d(3, 6, 3, padding=1)
+        self.classes_emb = nn.Embedding(config.data.n_classes, 6)
+        self.null_classes_emb = nn.Parameter(torch.randn(6))
+        self.temb = nn.Linear(1, 6)
+        self.conv_out = nn.Conv2d(6, 3, 3, padding=1)
+        TinyCond.instances.append(self)
+
+    def _forward(self, x, t, c, cond_drop_prob):
+        cemb = self.classes_emb(c)
+        if cond_drop_prob > 0:
+            keep = torch.rand(x.shape[0]) < (1 - cond_drop_prob)
+            cemb = torch.where(keep[:, None], cemb, self.null_classes_emb[None].expand_as(cemb))
+        h = self.conv_in(x) + (cemb + self.temb(t[:, None] / 1000.0))[:, :, None, None]
+        return self.conv_out(torch.tanh(h))
+
+    def forward(self, x, t, c, mode, **kwargs):
+        if mode == "train":
+            drop = kwargs.get("cond_drop_prob")
+            return self._forward(x, t, c, 0.1 if drop is None else drop)
+        scale = kwargs.get("cond_scale")
+        logits = self._forward(x, t, c, 0.0)
+        if scale == 0:
+            return logits
+        return (1 + scale) * logits - scale * self._forward(x, t, c, 1.0)
+
+
+class BackwardRecorder:
+    """Snapshots the raw gradient right after every `loss.backward()` (the runner calls
+    `optimizer.zero_grad()` before each one, so `.grad` is exactly that backward's result;
+    parameters the graph did not reach count as zero)."""
+
+    def __init__(self):
+        self.records = []
+        self._orig = torch.Tensor.backward
+
+    def __enter__(self):
+        rec = self
+
+        def backward(tensor, *a, **k):
+            out = rec._orig(tensor, *a, **k)
+            model = TinyCond.instances[0]
+            rec.records.append(flat([p.grad if p.grad is not None else torch.zeros_like(p)
+                                     for p in model.parameters()]))
+            return out
+        torch.Tensor.backward = backward
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.backward = self._orig
+
+
+def ddpm_runner():
+    import pickle  # noqa: F401  (the runner module imports it)
+    sys.path.insert(0, os.path.join(REF, "DDPM"))
+    import runners.diffusion as RD
+
+    def d2n(d):
+        ns = argparse.Namespace()
+        for k, v in d.items():
+            setattr(ns, k, d2n(v) if isinstance(v, dict) else v)
+        return ns
+
+    cfg = yaml.safe_load(open(os.path.join(REF, "DDPM/configs/cifar10_sfron.yml")))
+    cfg["data"]["image_size"] = 8
+    n_iters = 4
+    cfg["training"].update(n_iters=n_iters, snapshot_freq=n_iters, log_freq=10 ** 9,
+                           gamma=1.0, lmbda=1.0)          # only logged by generate_mask (:933)
+    config = d2n(cfg)
+
+    g = torch.Generator().manual_seed(21)
+    from torch.utils.data import DataLoader, TensorDataset
+    fx, fy = torch.rand(6, 3, 8, 8, generator=g), torch.zeros(6, dtype=torch.long)
+    rx, ry = torch.rand(9, 3, 8, 8, generator=g), torch.randint(1, 10, (9,), generator=g)
+    forget_loader = DataLoader(TensorDataset(fx, fy), batch_size=3, shuffle=False)     # 2 batches
+    remain_loader = DataLoader(TensorDataset(rx, ry), batch_size=3, shuffle=False)     # 3 batches
+    # shims: synthetic data, tiny network, no 1000-step sampling after the final snapshot
+    RD.get_forget_dataset = lambda args, config, label: (remain_loader, forget_loader)
+    RD.Conditional_Model = TinyCond
+    RD.Diffusion.sample_visualization = lambda self, *a, **k: None
+
+    torch.manual_seed(20)
+    init = nn.DataParallel(TinyCond(config))
+    names = [n for n, _ in init.named_parameters()]
+    shapes = {n: list(p.shape) for n, p in init.named_parameters()}
+    theta0 = flat(init.parameters())
+    fixture = dict(names=names, shapes=shapes, theta0=theta0, n_forget_batches=len(forget_loader),
+                   n_remain_batches=len(remain_loader),
+                   hyper=dict(lr=config.optim.lr, beta1=config.optim.beta1, beta2=0.999, eps=config.optim.eps,
+                              weight_decay=config.optim.weight_decay, grad_clip=config.optim.grad_clip,
+                              ema_rate=config.model.ema_rate, n_iters=n_iters))
+
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)                       # generate_mask writes to the cwd-relative results/cifar10/mask
+        try:
+            os.makedirs(os.path.join(tmp, "ckpts"))
+            from models.ema import EMAHelper
+            ema0 = EMAHelper(mu=config.model.ema_rate)
+            ema0.register(init)
+            torch.save([init.state_dict(), {}, 0, ema0.state_dict()], os.path.join(tmp, "ckpts/ckpt.pth"))
+            config.ckpt_dir = os.path.join(tmp, "out")
+            os.makedirs(config.ckpt_dir)
+
+            def run(method, seed, **over):
+                args = argparse.Namespace(ckpt_folder=tmp, label_to_forget=0, cond_scale=2.0, mask_path=None,
+                                          forget_alpha=1.0, decay_forget_alpha=False, remain_alpha=1.0,
+                                          method="ron", unlearn_loss="ga")
+                for k, v in over.items():
+                    setattr(args, k, v)
+                TinyCond.instances.clear()
+                torch.manual_seed(seed)
+                with BackwardRecorder() as rec:
+                    getattr(RD.Diffusion(args, config), method)()
+                return torch.stack(rec.records)
+
+            def final_state():
+                model_sd, opt_sd, step, ema_sd = torch.load(os.path.join(config.ckpt_dir, "ckpt.pth"),
+                                                            weights_only=False)
+                st = opt_sd["state"]
+                return dict(theta=flat([model_sd[n] for n in names]), step=int(step),
+                            exp_avg=flat([st[i]["exp_avg"] for i in range(len(names))]),
+                            exp_avg_sq=flat([st[i]["exp_avg_sq"] for i in range(len(names))]),
+                            opt_steps=[float(st[i]["step"]) for i in range(len(names))],
+                            ema=flat([ema_sd[n[len("module."):]] for n in names]),
+                            ckpt_model_keys=list(model_sd.keys()), ckpt_ema_keys=list(ema_sd.keys()),
+                            ckpt_opt_param_groups=opt_sd["param_groups"])
+
+            # --mode generate_fisher (runners/diffusion.py:1210-1364)
+            grads = run("generate_fisher", 31)
+            nf, nr = len(forget_loader), len(remain_loader)
+            assert len(grads) == nf + nr
+            mdir = os.path.join(tmp, "mask_0")
+            ff, rf = torch.load(os.path.join(mdir, "forget_fisher.pt")), torch.load(os.path.join(mdir, "remain_fisher.pt"))
+            assert list(ff.keys()) == names
+            fixture["fisher"] = dict(forget_grads=grads[:nf], remain_grads=grads[nf:],
+                                     forget_fisher=flat([ff[n] for n in names]),
+                                     remain_fisher=flat([rf[n] for n in names]))
+            # DDPM/generate_fisher_mask.py on those files (unmodified, as a subprocess)
+            subprocess.run([sys.executable, os.path.join(REF, "DDPM/generate_fisher_mask.py"), "--ckpt_folder", mdir,
+                            "--threshold", "1.0"], check=True, stdout=subprocess.DEVNULL)
+            ratio_path = os.path.join(mdir, "fisher_1.0.pt")
+            rmask = torch.load(ratio_path)
+            fixture["ratio_mask"] = torch.cat([rmask[n].reshape(-1) for n in names]).to(torch.uint8)
+            # --mode generate_mask (SalUn top-k, :930-1036)
+            grads = run("generate_mask", 32)
+            topk_path = os.path.join(tmp, "results/cifar10/mask/0/with_0.5.pt")
+            tmask = torch.load(topk_path)
+            assert list(tmask.keys()) == names and tmask[names[0]].dtype == torch.int64
+            fixture["topk"] = dict(grads=grads, mask=torch.cat([tmask[n].reshape(-1) for n in names]), ratio=0.5)
+            # --mode sfron (:1038-1208): ron, adaptive gradient ascent, cosine-decayed forget alpha, ratio mask
+            grads = run("sfron_forget", 33, mask_path=ratio_path, unlearn_loss="adaga", decay_forget_alpha=True,
+                        forget_alpha=5.0, remain_alpha=1.0)
+            assert len(grads) == 2 * n_iters
+            fixture["sfron"] = dict(grads=grads, kinds=["forget", "remain"] * n_iters, **final_state())
+            # --mode saliency_unlearn (:479-616): ONE joint step per iteration, clip BEFORE mask, top-k int64 mask
+            grads = run("saliency_unlearn", 34, mask_path=topk_path, unlearn_loss="rl", forget_alpha=0.3)
+            assert len(grads) == n_iters
+            fixture["salun"] = dict(grads=grads, **final_state())
+        finally:
+            os.chdir(cwd)
+    torch.save(fixture, os.path.join(OUT, "ddpm_runner.pt"))
+    print("wrote ddpm runner: N =", theta0.numel(), "fisher grads", nf + nr, "sfron records", 2 * n_iters)
+
+
 class TinyDiT(nn.Module):
     def __init__(self):
         super().__init__()
@@ -371,6 +551,7 @@ PARTS = {
                                     "nude_remain.pt", "nude_mask_{th}.pt", "sd", [1.0]),
     "dit_mask": dit_masks,
     "ddpm_loop": ddpm_loop,
+    "ddpm_runner": ddpm_runner,
     "dit_loop": dit_loop,
 }
 

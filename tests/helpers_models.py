@@ -25,6 +25,19 @@ class TinyDiT(nn.Module):
         self.out = nn.Linear(10, 4)
 
 
+class TinyCond(nn.Module):
+    """Parameter structure of the 411-parameter stand-in network make_golden.py's `ddpm_runner` part
+    gave the reference's Diffusion runner (named_parameters order: null_classes_emb first)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv_in = nn.Conv2d(3, 6, 3, padding=1)
+        self.classes_emb = nn.Embedding(10, 6)
+        self.null_classes_emb = nn.Parameter(torch.randn(6))
+        self.temb = nn.Linear(1, 6)
+        self.conv_out = nn.Conv2d(6, 3, 3, padding=1)
+
+
 def loaders(seed):
     g = torch.Generator().manual_seed(seed)
     fx, fy = torch.randn(12, 3, 8, 8, generator=g), torch.randint(0, 10, (12,), generator=g)

@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from conftest import load_golden, unflat
-from helpers_models import TinyDiT, TinyNet, inject, loaders
+from helpers_models import TinyCond, TinyDiT, TinyNet, inject, loaders
 
 pytestmark = pytest.mark.gpu
 
@@ -196,6 +196,75 @@ def test_ddpm_family_loop_fisher_and_topk(dev, tmp_path):
     import pickle
     with open(tmp_path / "fisher_dict.pkl", "rb") as f:
         assert list(pickle.load(f).keys()) == ["module." + n for n in sx["names"]]
+
+
+def test_ddpm_runner_dropin_against_whole_reference_methods(dev, tmp_path):
+    """The DDPM family of DiffusionUnlearner against `Diffusion.generate_fisher`, `generate_mask`,
+    `sfron_forget` and `saliency_unlearn` EXECUTED WHOLE from the reference (fixture ddpm_runner.pt):
+    the recorded raw gradient of every reference backward pass is replayed through a real backward."""
+    from sfron_b200.methods.diffusion import DiffusionUnlearner
+    from sfron_b200.methods.masks import generate_fisher_mask
+    fx = load_golden("ddpm_runner.pt")
+    h, pnames = fx["hyper"], fx["names"]
+    names = [n[len("module."):] for n in pnames]
+    shapes = {k[len("module."):]: v for k, v in fx["shapes"].items()}
+
+    def fresh():
+        model = TinyCond()
+        assert [n for n, _ in model.named_parameters()] == names
+        set_flat(model, fx["theta0"], names, shapes)
+        return DiffusionUnlearner(model.to(dev), "ddpm", lr=h["lr"])
+
+    def flat_of(d):
+        return torch.cat([d[n].reshape(-1) for n in pnames])
+
+    # --mode generate_fisher: Fisher of the clipped batch gradient, reference file names and keys
+    un, fi = fresh(), fx["fisher"]
+    un.generate_fisher("forget", len(fi["forget_grads"]), lambda i: inject(un.model, fi["forget_grads"][i]), out_dir=str(tmp_path))
+    un.generate_fisher("remain", len(fi["remain_grads"]), lambda i: inject(un.model, fi["remain_grads"][i]), out_dir=str(tmp_path))
+    ff = torch.load(tmp_path / "forget_fisher.pt", weights_only=False)
+    rf = torch.load(tmp_path / "remain_fisher.pt", weights_only=False)
+    assert list(ff.keys()) == pnames and list(rf.keys()) == pnames
+    assert close(flat_of(ff), fi["forget_fisher"]) and close(flat_of(rf), fi["remain_fisher"])
+    # generate_fisher_mask.py on the REFERENCE's Fisher files -> bit-exact bool mask, same file name
+    torch.save(unflat(fi["forget_fisher"], pnames, fx["shapes"]), tmp_path / "forget_fisher.pt")
+    torch.save(unflat(fi["remain_fisher"], pnames, fx["shapes"]), tmp_path / "remain_fisher.pt")
+    path = generate_fisher_mask(str(tmp_path), 1.0)
+    assert os.path.basename(path) == "fisher_1.0.pt"
+    rmask = torch.load(path, weights_only=False)
+    assert rmask[pnames[0]].dtype == torch.bool
+    assert torch.equal(flat_of(rmask).to(torch.uint8), fx["ratio_mask"])
+    # --mode generate_mask: SalUn top-k of |sum of clipped gradients| -> int64 0/1, bit-exact
+    un, tk = fresh(), fx["topk"]
+    hard = un.generate_topk_mask(len(tk["grads"]), lambda i: inject(un.model, tk["grads"][i]), ratio=tk["ratio"],
+                                 path=str(tmp_path / "results" / "with_0.5.pt"))
+    got = flat_of(hard)
+    assert got.dtype == torch.int64 and torch.equal(got.cpu(), tk["mask"])
+
+    def check_final(un, rec, n_steps):
+        final = torch.cat([p.detach().reshape(-1) for p in un.model.parameters()])
+        assert close(final, rec["theta"])
+        states = un.checkpoint(step=rec["step"])
+        assert list(states[0].keys()) == rec["ckpt_model_keys"] and list(states[3].keys()) == rec["ckpt_ema_keys"]
+        assert close(torch.cat([states[3][n].reshape(-1) for n in names]), rec["ema"])
+        st = states[1]["state"]
+        assert close(torch.cat([st[i]["exp_avg"].reshape(-1) for i in range(len(names))]), rec["exp_avg"])
+        assert close(torch.cat([st[i]["exp_avg_sq"].reshape(-1) for i in range(len(names))]), rec["exp_avg_sq"])
+        assert [float(st[i]["step"]) for i in range(len(names))] == rec["opt_steps"] == [float(n_steps)] * len(names)
+        assert states[1]["param_groups"] == rec["ckpt_opt_param_groups"]      # loadable by the reference's optimizer
+
+    # --mode sfron (ron): alpha_t is already inside the recorded forget gradients
+    un, rec = fresh(), fx["sfron"]
+    un.load_mask(path)
+    gf, gr = rec["grads"][0::2], rec["grads"][1::2]
+    assert rec["kinds"][0::2] == ["forget"] * len(gf)
+    un.forget(len(gf), lambda i: inject(un.model, gf[i]), lambda i: inject(un.model, gr[i]))
+    check_final(un, rec, 2 * len(gf))
+    # --mode saliency_unlearn: joint loss, clip BEFORE the int64 top-k mask
+    un, rec = fresh(), fx["salun"]
+    un.load_mask(unflat(fx["topk"]["mask"], pnames, fx["shapes"]))
+    un.saliency_unlearn(len(rec["grads"]), lambda i: inject(un.model, rec["grads"][i]))
+    check_final(un, rec, len(rec["grads"]))
 
 
 def test_bf16_model_mixed_precision_flat_params(dev):

@@ -116,3 +116,79 @@ def test_dit_adamw_ema_loop():
     assert _close(got_e, fx["ema_final"])
     for t, ref in enumerate(fx["cosine"]):
         assert O.cosine_lr_scheduler(25.0, t, 10) == ref
+
+
+def _runner_fixture():
+    fx = load_golden("ddpm_runner.pt")
+    return fx, fx["names"], fx["shapes"], fx["hyper"]
+
+
+def test_ddpm_runner_fisher_and_masks():
+    """Diffusion.generate_fisher / generate_fisher_mask.py / Diffusion.generate_mask executed whole
+    (DDPM/runners/diffusion.py:1210-1364, 930-1036) — Fisher of the CLIPPED batch gradient."""
+    fx, names, shapes, hp = _runner_fixture()
+    fi = fx["fisher"]
+    fishers = {}
+    for which, n_batches in (("forget", fx["n_forget_batches"]), ("remain", fx["n_remain_batches"])):
+        acc = O.fisher_init(names)
+        for g in fi[f"{which}_grads"]:
+            O.fisher_accumulate_clipped(acc, unflat(g, names, shapes), n_batches, hp["grad_clip"])
+        fishers[which] = acc
+        got = torch.cat([acc[n].reshape(-1) for n in names])
+        assert bits_equal(got, fi[f"{which}_fisher"]), which
+    masks, _, _ = O.ratio_mask(unflat(fi["forget_fisher"], names, shapes), unflat(fi["remain_fisher"], names, shapes), 1.0)
+    assert torch.equal(torch.cat([masks[n].reshape(-1) for n in names]).to(torch.uint8), fx["ratio_mask"])
+    # SalUn top-k: sum of the clipped gradients, abs, global rank (:985-1034)
+    tk = fx["topk"]
+    tot = {n: 0 for n in names}
+    for g in tk["grads"]:
+        gd = unflat(g, names, shapes)
+        O.clip_grad_norm(list(gd.values()), hp["grad_clip"])
+        for n in names:
+            tot[n] = tot[n] + gd[n]
+    hard = O.topk_mask({n: t.abs() for n, t in tot.items()}, tk["ratio"])
+    got = torch.cat([hard[n].reshape(-1) for n in names])
+    assert got.dtype == torch.int64 and torch.equal(got, tk["mask"])
+
+
+def _runner_loop(fx, names, shapes, hp):
+    return O.FlatReferenceLoop(shapes, unflat(fx["theta0"], names, shapes), "adam",
+                               dict(lr=hp["lr"], beta1=hp["beta1"], beta2=hp["beta2"], eps=hp["eps"],
+                                    weight_decay=hp["weight_decay"]), ema_mode="ddpm", ema_a=hp["ema_rate"])
+
+
+def _check_runner_final(loop, rec):
+    assert _close(loop.flat("p"), rec["theta"])
+    assert _close(loop.flat("m"), rec["exp_avg"])
+    assert _close(loop.flat("v"), rec["exp_avg_sq"])
+    assert _close(loop.flat("slow"), rec["ema"])
+
+
+def test_ddpm_runner_sfron_forget():
+    """Diffusion.sfron_forget executed whole (method ron, adaga, decayed alpha, ratio mask; :1038-1208)."""
+    fx, names, shapes, hp = _runner_fixture()
+    rec = fx["sfron"]
+    loop = _runner_loop(fx, names, shapes, hp)
+    mask = {n: m.bool() for n, m in unflat(fx["ratio_mask"], names, shapes).items()}
+    for kind, g in zip(rec["kinds"], rec["grads"]):
+        gd = unflat(g, names, shapes)
+        if kind == "forget":
+            loop.forget_step(gd, mask=mask, max_norm=hp["grad_clip"])
+        else:
+            loop.remain_step(gd, max_norm=hp["grad_clip"], ema=True)
+    _check_runner_final(loop, rec)
+    assert rec["step"] == hp["n_iters"] - 1 and set(rec["opt_steps"]) == {2.0 * hp["n_iters"]}
+    assert rec["ckpt_model_keys"] == names and rec["ckpt_ema_keys"] == [n[len("module."):] for n in names]
+
+
+def test_ddpm_runner_saliency_unlearn():
+    """Diffusion.saliency_unlearn executed whole: one joint step per iteration, clip BEFORE the int64
+    top-k mask, then EMA (:479-616)."""
+    fx, names, shapes, hp = _runner_fixture()
+    rec = fx["salun"]
+    loop = _runner_loop(fx, names, shapes, hp)
+    mask = unflat(fx["topk"]["mask"], names, shapes)
+    for g in rec["grads"]:
+        loop.forget_step(unflat(g, names, shapes), mask=mask, max_norm=hp["grad_clip"], order="clip_then_mask")
+        loop.slow_update()
+    _check_runner_final(loop, rec)

@@ -11,6 +11,7 @@ Reference order of operations:
             top-k of |sum grad|                  SalUn              -> topk_mask()
   forget    grad *= mask ; clip ; optimizer.step                    -> forget_step()
   remain    [clip ;] optimizer.step ; EMA / slow-fast               -> remain_step()
+  SalUn     clip ; grad *= mask ; optimizer.step ; EMA (joint loss) -> joint_step()
 One optimizer state serves both steps (`step` advances twice per iteration), exactly as the
 single torch optimizer object of every reference loop.
 """
@@ -310,6 +311,17 @@ class HotPath:
         (sfron.py:213-222,255-257; runners/diffusion.py:1156-1180; DiT/forget.py:310-322)."""
         self._step(p, g, mask=None, mask_order="mask_then_clip", max_norm=max_norm, ema=ema, lr=lr,
                    zero_grad=zero_grad, p_bf16=p_bf16)
+
+    def joint_step(self, p: torch.Tensor, g: torch.Tensor, *, mask: Optional[torch.Tensor] = None,
+                   use_mask: bool = True, max_norm: Optional[float] = None, lr: Optional[float] = None,
+                   mask_order: str = "clip_then_mask", ema: bool = True, zero_grad: bool = False,
+                   p_bf16: Optional[torch.Tensor] = None) -> None:
+        """SalUn's single step on the joint forget+remain loss: clip_grad_norm_ ; grad *= mask ;
+        optimizer.step() ; EMA (runners/diffusion.py:575-594 — the clip precedes the mask there)."""
+        if mask is None and use_mask:
+            mask = self.mask
+        self._step(p, g, mask=mask if use_mask else None, mask_order=mask_order, max_norm=max_norm,
+                   ema=ema, lr=lr, zero_grad=zero_grad, p_bf16=p_bf16)
 
     def grad_norm(self) -> torch.Tensor:
         """Total norm of the last clipped step (what clip_grad_norm_ returns), fp32 device scalar."""

@@ -109,6 +109,14 @@ class ModelHotPath:
         if ema and self.frozen_slow is not None:
             self.hp.ema_only(self.flat.frozen, self.frozen_slow)
 
+    def joint_step(self, *, use_mask: bool = True, max_norm: Optional[float] = None, lr: Optional[float] = None,
+                   mask_order: str = "clip_then_mask", ema: bool = True) -> None:
+        self.hp.joint_step(self.flat.p, self.grads(), use_mask=use_mask, max_norm=max_norm, lr=lr,
+                           mask_order=mask_order, ema=ema, zero_grad=self.flat.grads_as_views,
+                           p_bf16=self.flat.p_work)
+        if ema and self.frozen_slow is not None:
+            self.hp.ema_only(self.flat.frozen, self.frozen_slow)
+
     # ---- state export ------------------------------------------------------------------------------
     def slow_state_dict(self) -> Dict[str, torch.Tensor]:
         """EMA shadow / slow weights per parameter name (EMAHelper.state_dict(), ema.state_dict())."""

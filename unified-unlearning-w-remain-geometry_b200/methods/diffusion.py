@@ -186,6 +186,22 @@ class DiffusionUnlearner:
             if log_every and (step + 1) % log_every == 0:
                 print(f"step:{step:04d} forget a:{alpha:.8f}")
 
+    def saliency_unlearn(self, n_iters: int, joint_loss_fn: LossFn, *, use_mask: bool = True,
+                         log_every: int = 0) -> None:
+        """SalUn loop of DDPM `--mode saliency_unlearn` (runners/diffusion.py:518-594): ONE backward per
+        iteration on `forget_alpha * forget_loss + remain_alpha * remain_loss` (the closure returns that
+        sum), then clip -> mask -> optimizer.step -> EMA.  Note the order: unlike SFR-on, the reference
+        clips the unmasked gradient and masks afterwards."""
+        mhp, cfg = self.mhp, self.cfg
+        mhp.zero_grad()
+        self.model.train()
+        for step in range(n_iters):
+            loss = joint_loss_fn(step)
+            loss.backward()
+            mhp.joint_step(use_mask=use_mask, max_norm=cfg.clip_remain, mask_order="clip_then_mask", ema=True)
+            if log_every and (step + 1) % log_every == 0:
+                print(f"step: {step}, loss: {float(loss)}")
+
     # ---- consumers next to the path (SURVEY.md §8f n2, n3) -------------------------------------------
     def snapshot_params(self, role: str = "params_mle") -> torch.Tensor:
         """`params_mle_dict[name] = param.data.clone()` (runners/diffusion.py:391-393) /
