@@ -278,7 +278,8 @@ def run_ours(args, rank, world, local_rank):
             times.append(a.elapsed_time(b))
         ms = sorted(times)[1]
         extra["topk_select_k_half"] = {"ms": round(ms, 4), "GBps": round(13 * n / (ms * 1e-3) / 1e9, 1),
-                                       "bytes_per_elem": 13, "selected": int(topk.sum(dtype=torch.int64))}
+                                       "bytes_per_elem": 13, "traffic_bytes_per_elem": 9,
+                                       "selected": int(topk.sum(dtype=torch.int64))}
         del topk
 
     # ---- e2e: gradients from pinned host memory, scalars read back, through the public API ------------

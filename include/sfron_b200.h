@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SFR_ABI_VERSION 1
+#define SFR_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SFR_API __attribute__((visibility("default")))
@@ -126,6 +126,7 @@ SFR_API int sfr_ratio_mask_multi(const float* ff, const float* rf, int64_t n,
  *   [all-reduce(sum) bins over ranks]
  *   sfr_select_scan(pass = 0)   -> state: 15-bit prefix, k remaining inside that bin
  *   sfr_select_hist(pass = 1)   -> bins[0 .. SFR_SELECT_BINS1)    (only keys matching prefix)
+ *     or sfr_select_hist1_mask  -> the same, plus the provisional mask (see below)
  *   [all-reduce(sum) bins over ranks]
  *   sfr_select_scan(pass = 1)   -> state: thr_key, count_gt, count_eq, tie_budget
  *   sfr_select_apply            -> mask
@@ -162,6 +163,15 @@ SFR_API int sfr_select_hist(const float* a, const float* b, int key_mode, float 
                     int64_t n, int pass, const sfr_select_state* state_dev,
                     unsigned long long* bins_dev, unsigned long long* scratch_dev,
                     sfr_stream_t stream);
+/* Pass 1 that ALSO writes a provisional mask (1 where key[30:16] > the chosen prefix, else 0): final for
+ * every element except the staged candidates.  A following sfr_select_apply on the SAME mask and scratch then
+ * finishes the mask from the candidate list alone — the select reads the vector twice instead of three times
+ * (4 + 4 + 1 B/elem).  If a candidate region overflows, or apply is given another mask buffer, apply falls
+ * back to its full streaming pass; results are identical either way. */
+SFR_API int sfr_select_hist1_mask(const float* a, const float* b, int key_mode, float eps,
+                    int64_t n, const sfr_select_state* state_dev,
+                    unsigned long long* bins_dev, unsigned long long* scratch_dev,
+                    uint8_t* mask, sfr_stream_t stream);
 SFR_API int sfr_select_scan(int pass, sfr_select_state* state_dev,
                     unsigned long long* bins_dev, sfr_stream_t stream);
 /* tie_base_dev: device u64 (NULL = 0).  scratch_dev: the SAME device u64 array of at least

@@ -174,9 +174,42 @@ def test_k2a_golden_classification_mask(sfr, dev):
 
 # =============================================================================== K2b top-k select
 def run_topk(sfr, dev, values, k, other=None):
+    """Runs BOTH forms of the select on a garbage-filled mask buffer — the two-pass form (pass 1 leaves the
+    provisional mask, apply resolves the staged candidates) and the three-read form (streaming apply) — and
+    requires identical bytes; returns the two-pass result."""
     hp = sfr.HotPath(values.numel(), dev, sfr.OptConfig())
-    mask = hp.topk_mask(values.to(dev), k, other=None if other is None else other.to(dev))
-    return mask.cpu(), hp.select_state()
+    v, o = values.to(dev), None if other is None else other.to(dev)
+    out = {}
+    for two_pass in (False, True):
+        hp.select_two_pass = two_pass
+        buf = torch.full((values.numel(),), 0xCC, dtype=torch.uint8, device=dev)
+        out[two_pass] = hp.topk_mask(v, k, other=o, out=buf).cpu()
+    assert torch.equal(out[True], out[False]), "two-pass and three-read selects disagree"
+    return out[True], hp.select_state()
+
+
+def test_k2b_two_pass_apply_on_another_mask_buffer_falls_back(sfr, dev):
+    """sfr_select_apply given a mask buffer other than the one pass 1 wrote must not trust the provisional
+    mask: it streams the vector and still produces the exact result; repeating apply is idempotent."""
+    n, k = 300_007, 120_000
+    x = torch.randn(n, generator=gen(11)) * 1e-2
+    x[::7] = x[3]                                   # ties at a value near the threshold region
+    xd = x.to(dev)
+    hp = sfr.HotPath(n, dev, sfr.OptConfig())
+    state, bins, scratch = hp._select_buffers()
+    capi = sfr.capi
+    first = torch.full((n,), 0xCC, dtype=torch.uint8, device=dev)
+    other = torch.full((n,), 0xCC, dtype=torch.uint8, device=dev)
+    capi.select_init(state, bins, k)
+    capi.select_hist(xd, None, capi.KEY_ABS, 0, state, bins)
+    capi.select_scan(0, state, bins)
+    capi.select_hist(xd, None, capi.KEY_ABS, 1, state, bins, scratch, mask=first)
+    capi.select_scan(1, state, bins)
+    capi.select_apply(xd, None, capi.KEY_ABS, state, None, scratch, other)      # not the pass-1 buffer
+    capi.select_apply(xd, None, capi.KEY_ABS, state, None, scratch, first)
+    capi.select_apply(xd, None, capi.KEY_ABS, state, None, scratch, first)      # again: idempotent
+    ref = O.topk_mask_flat(x, k)
+    assert torch.equal(other.cpu(), ref) and torch.equal(first.cpu(), ref)
 
 
 def test_k2b_golden_salun(sfr, dev):

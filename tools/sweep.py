@@ -130,7 +130,13 @@ def main():
             topk = torch.empty(n, dtype=torch.uint8, device=dev)
             k = n // 2
             emit("topk_select_total", n, "-", 13, timer(lambda: hp.topk_mask(g32, k, out=topk)),
-                 note="hist pass 0 + pass 1 + apply = 4+4+4+1 B/elem")
+                 note="two-pass form: pass 1 writes the provisional mask, apply resolves the staged candidates; "
+                      "13 B/elem is the three-read algorithmic figure, actual traffic ~9 B/elem")
+            assert int(topk.sum()) == k
+            hp.select_two_pass = False
+            emit("topk_select_total_three_reads", n, "-", 13, timer(lambda: hp.topk_mask(g32, k, out=topk)),
+                 note="hist pass 0 + pass 1 + streaming apply = 4+4+4+1 B/elem")
+            hp.select_two_pass = True
             capi.select_init(state, bins, k)
             emit("topk_hist_pass0", n, "-", 4,
                  timer(lambda: capi.select_hist(g32, None, capi.KEY_ABS, 0, state, bins)))
@@ -143,6 +149,18 @@ def main():
             capi.select_hist(g32, None, capi.KEY_ABS, 1, state, bins, scratch)
             capi.select_scan(1, state, bins)
             emit("topk_apply", n, "-", 5,
+                 timer(lambda: capi.select_apply(g32, None, capi.KEY_ABS, state, None, scratch, topk)))
+            assert int(topk.sum()) == k
+            # the two-pass form: pass 1 with the provisional mask, then the candidate-only apply
+            capi.select_init(state, bins, k)
+            capi.select_hist(g32, None, capi.KEY_ABS, 0, state, bins)
+            capi.select_scan(0, state, bins)
+            emit("topk_hist_pass1_with_mask", n, "-", 5,
+                 timer(lambda: capi.select_hist(g32, None, capi.KEY_ABS, 1, state, bins, scratch, mask=topk)))
+            bins.zero_()
+            capi.select_hist(g32, None, capi.KEY_ABS, 1, state, bins, scratch, mask=topk)
+            capi.select_scan(1, state, bins)
+            emit("topk_apply_candidates_only", n, "-", 0,
                  timer(lambda: capi.select_apply(g32, None, capi.KEY_ABS, state, None, scratch, topk)))
             assert int(topk.sum()) == k
             del topk

@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsfron_b200.so")
 
 # ---- constants mirrored from include/sfron_b200.h ---------------------------------------
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, ERR_NULL, ERR_ALIGN, ERR_ARG, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 F32, BF16 = 0, 1
 KEY_ABS, KEY_RATIO, KEY_ABSDIFF = 0, 1, 2
@@ -31,7 +31,7 @@ F_MASK, F_MASK_AFTER_CLIP, F_ZERO_GRAD, F_SGD_FIRST_STEP, F_WRITE_BF16 = 1, 2, 4
 
 EXPORTED_SYMBOLS = (
     "sfr_abi_version", "sfr_error_string", "sfr_device_info", "sfr_fisher_accum",
-    "sfr_ratio_mask", "sfr_ratio_mask_multi", "sfr_select_init", "sfr_select_hist",
+    "sfr_ratio_mask", "sfr_ratio_mask_multi", "sfr_select_init", "sfr_select_hist", "sfr_select_hist1_mask",
     "sfr_select_scan", "sfr_select_scratch_elems", "sfr_select_apply", "sfr_masked_sumsq",
     "sfr_fused_update", "sfr_ema_update", "sfr_gather_segments",
     "sfr_ewc_penalty", "sfr_select_threshold_value", "sfr_soft_threshold",
@@ -99,6 +99,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.sfr_select_init.argtypes = [vp, vp, u64, vp]
     lib.sfr_select_hist.restype = C.c_int
     lib.sfr_select_hist.argtypes = [vp, vp, C.c_int, f32, i64, C.c_int, vp, vp, vp, vp]
+    lib.sfr_select_hist1_mask.restype = C.c_int
+    lib.sfr_select_hist1_mask.argtypes = [vp, vp, C.c_int, f32, i64, vp, vp, vp, vp, vp]
     lib.sfr_select_scan.restype = C.c_int
     lib.sfr_select_scan.argtypes = [C.c_int, vp, vp, vp]
     lib.sfr_select_scratch_elems.restype = i64
@@ -219,9 +221,19 @@ def select_init(state: torch.Tensor, bins: torch.Tensor, k: int) -> None:
 
 def select_hist(a: torch.Tensor, b: Optional[torch.Tensor], key_mode: int, pass_: int,
                 state: torch.Tensor, bins: torch.Tensor, scratch: Optional[torch.Tensor] = None,
-                eps: float = 1e-15) -> None:
+                eps: float = 1e-15, mask: Optional[torch.Tensor] = None) -> None:
+    """`mask` (pass 1 only): also write the provisional mask there, so that `select_apply` on the same mask
+    finishes from the staged candidates without a third pass over the vector."""
     if scratch is not None and scratch.numel() < select_scratch_elems(a.numel()):
         raise SfrError(ERR_ARG, "select_hist", "scratch too small")
+    if mask is not None:
+        if pass_ != 1 or mask.numel() != a.numel():
+            raise SfrError(ERR_ARG, "select_hist", "mask is a pass-1 output of the same length as the keys")
+        _check(load().sfr_select_hist1_mask(_ptr(a, torch.float32, "a"), _ptr(b, torch.float32, "b"), key_mode,
+                                            float(eps), a.numel(), _ptr(state, torch.int64, "state"),
+                                            _ptr(bins, torch.int64, "bins"), _ptr(scratch, torch.int64, "scratch"),
+                                            _ptr(mask, _MASK_DTYPES, "mask"), _stream()), "sfr_select_hist1_mask")
+        return
     _check(load().sfr_select_hist(_ptr(a, torch.float32, "a"), _ptr(b, torch.float32, "b"), key_mode,
                                   float(eps), a.numel(), pass_, _ptr(state, torch.int64, "state"),
                                   _ptr(bins, torch.int64, "bins"), _ptr(scratch, torch.int64, "scratch"),

@@ -13,6 +13,9 @@
 //           only the few matching elements issue an atomic)
 //   scan 1: threshold key, #greater, #equal, tie budget
 //   apply : mask = key > thr  ||  (key == thr && index-ordered tie rank < budget)
+//           With sfr_select_hist1_mask, pass 1 already wrote mask = key[30:16] > prefix for every
+//           element and staged the few keys that share the prefix; apply then only walks that list
+//           (and re-reads the handful of chunks holding an ordered tie): 4 + 4 + 1 B/elem in all.
 // Between hist and scan a multi-GPU caller all-reduces `bins` (<= 512 KB) over NCCL;
 // everything else is shard-local.  All steps are stream-ordered; the host never has to
 // read anything back.
@@ -117,6 +120,7 @@ select_hist0_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
 //   [nchunks, 2*nchunks)          per scan block (kScanBlock chunks): exclusive tie base (+ tie_base);
 //                                 only the first ceil(nchunks / kScanBlock) words are used
 //   header (kCandHeader words):   [0] overflow flag, [1] number of regions, [2] region capacity,
+//                                 [3] 1 if pass 1 also wrote the provisional mask, [4] that mask's address,
 //                                 [8 + r] entries staged in region r
 //   candidate regions             cand_cap words: (flat index << 16) | key[15:0]
 constexpr int64_t kChunkElems = 8192;       // == kChunk below (kApplyThreads * 4 * kChunkVecs)
@@ -153,11 +157,15 @@ struct CandStage {
   }
 };
 
-template <int MODE>
+// With WRITE the pass also leaves a PROVISIONAL mask: 1 where key[30:16] > prefix, 0 elsewhere — final
+// for every element except the staged ones, which sfr_select_apply then resolves from the candidate
+// list alone (no third pass over the vector).
+template <int MODE, bool WRITE>
 __global__ void __launch_bounds__(kFiltThreads, kFiltCtasPerSm)
 select_hist1_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps, int64_t n,
                     const sfr_select_state* __restrict__ state,
-                    unsigned long long* __restrict__ bins, unsigned long long* __restrict__ scratch) {
+                    unsigned long long* __restrict__ bins, unsigned long long* __restrict__ scratch,
+                    uint8_t* __restrict__ mask) {
   if (state->select_none || state->select_all) return;
   __shared__ unsigned int s_count, s_over;
   if (threadIdx.x == 0) {
@@ -205,6 +213,11 @@ select_hist1_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
       if ((k1 >> 16) == prefix) { rc.push(bins, k1 & 0xffffu); cs.push(v * 4 + 1, k1); }
       if ((k2 >> 16) == prefix) { rc.push(bins, k2 & 0xffffu); cs.push(v * 4 + 2, k2); }
       if ((k3 >> 16) == prefix) { rc.push(bins, k3 & 0xffffu); cs.push(v * 4 + 3, k3); }
+      if constexpr (WRITE) {
+        const uint32_t s0 = (k0 >> 16) > prefix, s1 = (k1 >> 16) > prefix;
+        const uint32_t s2 = (k2 >> 16) > prefix, s3 = (k3 >> 16) > prefix;
+        reinterpret_cast<unsigned int*>(mask)[v] = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+      }
     }
   }
   const int64_t tail0 = nvec << 2;
@@ -212,6 +225,7 @@ select_hist1_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
     const int64_t i = tail0 + threadIdx.x;
     const uint32_t k = key_from<MODE>(a[i], MODE != SFR_KEY_ABS ? b[i] : 0.f, eps);
     if ((k >> 16) == prefix) { rc.push(bins, k & 0xffffu); cs.push(i, k); }
+    if constexpr (WRITE) mask[i] = (uint8_t)((k >> 16) > prefix);
   }
   rc.flush(bins);
   __syncthreads();
@@ -221,6 +235,10 @@ select_hist1_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
     if (blockIdx.x == 0) {
       hdr[1] = gridDim.x;
       hdr[2] = cs.cap;
+      if constexpr (WRITE) {
+        hdr[3] = 1ull;
+        hdr[4] = (unsigned long long)(uintptr_t)mask;
+      }
     }
   }
 }
@@ -346,6 +364,12 @@ __device__ __forceinline__ bool ties_need_order(const sfr_select_state* s) {
   return !s->select_none && !s->select_all && s->tie_budget != s->count_eq;
 }
 
+// The candidate list is complete (no region overflowed) and pass 1 left the provisional mask in THIS
+// mask buffer: only the staged candidates (and the chunks that hold an ordered tie) remain to be written.
+__device__ __forceinline__ bool provisional_ok(const unsigned long long* hdr, const uint8_t* mask) {
+  return hdr[0] == 0ull && hdr[3] == 1ull && hdr[4] == (unsigned long long)(uintptr_t)mask;
+}
+
 // Keys of one chunk, all loads issued before the first use.  A chunk is kChunkVecs slabs of
 // kApplyThreads float4; thread t owns elements [base + (slab*256 + t)*4, +4), so flat order ==
 // (slab, thread, component) order.  Out-of-range elements get key 0 and valid bit 0.
@@ -411,13 +435,18 @@ select_tie_count_kernel(const float* __restrict__ a, const float* __restrict__ b
 
 // Per-chunk tie counts from the staged candidates (the usual path): every region is scanned by
 // one CTA; only entries whose low key bits equal the threshold's touch a (zeroed) chunk counter.
+// When pass 1 left a provisional mask, the same walk also FINISHES the mask for the candidates: low bits
+// above the threshold's -> 1; equal -> 1 if every tie is selected, else left 0 for the ordered kernel.
 __global__ void __launch_bounds__(256, 8)
-select_tie_count_candidates_kernel(int64_t n, const sfr_select_state* __restrict__ state,
-                                   unsigned long long* __restrict__ scratch) {
-  if (!ties_need_order(state)) return;
+select_resolve_candidates_kernel(int64_t n, const sfr_select_state* __restrict__ state,
+                                 unsigned long long* __restrict__ scratch, uint8_t* __restrict__ mask) {
+  if (state->select_none || state->select_all) return;
   const int64_t nchunks = (n + kChunk - 1) / kChunk;
   const unsigned long long* hdr = scratch + 2 * nchunks;
-  if (hdr[0] != 0ull) return;  // overflow: the streaming kernel counts instead
+  if (hdr[0] != 0ull) return;  // overflow: the streaming kernels count and write instead
+  const bool order = ties_need_order(state);
+  const bool write = provisional_ok(hdr, mask);
+  if (!order && !write) return;
   const unsigned int thr16 = state->thr_key & 0xffffu;
   const int regions = (int)hdr[1];
   const unsigned long long cap = hdr[2];
@@ -426,7 +455,13 @@ select_tie_count_candidates_kernel(int64_t n, const sfr_select_state* __restrict
     const unsigned int cnt = (unsigned int)hdr[8 + r];
     for (unsigned int i = threadIdx.x; i < cnt; i += blockDim.x) {
       const unsigned long long e = region[i];
-      if ((unsigned int)(e & 0xffffull) == thr16) atomicAdd(scratch + (e >> 16) / kChunk, 1ull);
+      const unsigned int low = (unsigned int)(e & 0xffffull);
+      if (low == thr16) {
+        if (order) atomicAdd(scratch + (e >> 16) / kChunk, 1ull);
+        else mask[e >> 16] = 1;            // write is true here
+      } else if (write && low > thr16) {
+        mask[e >> 16] = 1;
+      }
     }
   }
 }
@@ -502,10 +537,12 @@ template <int MODE>
 __global__ void __launch_bounds__(kApplyThreads, 4)
 select_apply_stream_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps,
                            int64_t n, const sfr_select_state* __restrict__ state,
-                           uint8_t* __restrict__ mask) {
+                           const unsigned long long* __restrict__ scratch, uint8_t* __restrict__ mask) {
   if (ties_need_order(state)) return;  // the ordered kernel below writes the mask instead
   const bool none = state->select_none != 0;
   const bool all = state->select_all != 0;
+  // pass 1's provisional mask + the candidate walk already produced the whole mask
+  if (!none && !all && provisional_ok(scratch + 2 * scratch_nchunks(n), mask)) return;
   const uint32_t thr = all ? 0u : state->thr_key;  // all: every key (NaN's 0 included) >= 0
   const int64_t nvec = n >> 2;
   const int64_t tile = (int64_t)kApplyThreads * kApplyUnroll;
@@ -556,10 +593,13 @@ select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
   const unsigned long long budget = state->tie_budget;
   const int64_t nchunks = (n + kChunk - 1) / kChunk;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // provisional mask in place: only the chunks that hold a threshold-equal key are rewritten
+  const bool only_tie_chunks = provisional_ok(scratch + 2 * nchunks, mask);
 
   for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const int64_t base = c * kChunk;
     const unsigned long long chunk_ties = scratch[c];        // uniform over the CTA
+    if (chunk_ties == 0 && only_tie_chunks) continue;
     if (chunk_ties == 0 && base + kChunk <= n) {
       // tie-free full chunk (almost all of them): straight-line stream, mask = key > thr
       float4 x[kChunkVecs], y[kChunkVecs];
@@ -666,10 +706,10 @@ extern "C" int sfr_select_init(sfr_select_state* state, unsigned long long* bins
   SFR_LAUNCH_STATUS();
 }
 
-extern "C" int sfr_select_hist(const float* a, const float* b, int key_mode, float eps,
-                               int64_t n, int pass, const sfr_select_state* state,
-                               unsigned long long* bins, unsigned long long* scratch,
-                               sfr_stream_t stream) {
+static int select_hist_impl(const float* a, const float* b, int key_mode, float eps,
+                            int64_t n, int pass, const sfr_select_state* state,
+                            unsigned long long* bins, unsigned long long* scratch,
+                            uint8_t* mask, sfr_stream_t stream) {
   using namespace sfr;
   if (n < 0 || (pass != 0 && pass != 1)) return SFR_ERR_ARG;
   if (key_mode < SFR_KEY_ABS || key_mode > SFR_KEY_ABSDIFF) return SFR_ERR_ARG;
@@ -704,11 +744,36 @@ extern "C" int sfr_select_hist(const float* a, const float* b, int key_mode, flo
     if (grid > kMaxRegions) grid = kMaxRegions;
     // zero the per-chunk tie counters and the candidate header (the regions need no clearing)
     cudaMemsetAsync(scratch, 0, (size_t)(2 * scratch_nchunks(n) + kCandHeader) * sizeof(unsigned long long), s);
-    if (key_mode == SFR_KEY_ABS) select_hist1_kernel<SFR_KEY_ABS><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins, scratch);
-    else if (key_mode == SFR_KEY_RATIO) select_hist1_kernel<SFR_KEY_RATIO><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins, scratch);
-    else select_hist1_kernel<SFR_KEY_ABSDIFF><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins, scratch);
+#define SFR_HIST1(M)                                                                                          \
+  do {                                                                                                        \
+    if (mask) select_hist1_kernel<M, true><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins, scratch, mask); \
+    else select_hist1_kernel<M, false><<<grid, kFiltThreads, 0, s>>>(a, b, eps, n, state, bins, scratch, nullptr);  \
+  } while (0)
+    if (key_mode == SFR_KEY_ABS) SFR_HIST1(SFR_KEY_ABS);
+    else if (key_mode == SFR_KEY_RATIO) SFR_HIST1(SFR_KEY_RATIO);
+    else SFR_HIST1(SFR_KEY_ABSDIFF);
+#undef SFR_HIST1
   }
   SFR_LAUNCH_STATUS();
+}
+
+extern "C" int sfr_select_hist(const float* a, const float* b, int key_mode, float eps,
+                               int64_t n, int pass, const sfr_select_state* state,
+                               unsigned long long* bins, unsigned long long* scratch,
+                               sfr_stream_t stream) {
+  return select_hist_impl(a, b, key_mode, eps, n, pass, state, bins, scratch, nullptr, stream);
+}
+
+extern "C" int sfr_select_hist1_mask(const float* a, const float* b, int key_mode, float eps,
+                                     int64_t n, const sfr_select_state* state,
+                                     unsigned long long* bins, unsigned long long* scratch,
+                                     uint8_t* mask, sfr_stream_t stream) {
+  using namespace sfr;
+  if (n > 0) {
+    SFR_REQUIRE_PTR(mask);
+    SFR_REQUIRE_ALIGNED(mask);
+  }
+  return select_hist_impl(a, b, key_mode, eps, n, 1, state, bins, scratch, mask, stream);
 }
 
 extern "C" int sfr_select_scan(int pass, sfr_select_state* state, unsigned long long* bins,
@@ -754,14 +819,14 @@ extern "C" int sfr_select_apply(const float* a, const float* b, int key_mode, fl
   const int sgrid = persistent_grid(((n >> 2) + stile - 1) / stile, 4);
   // the per-chunk counters are accumulated into: clear them here so that apply is idempotent
   cudaMemsetAsync(scratch, 0, (size_t)nchunks * sizeof(unsigned long long), s);
-  select_tie_count_candidates_kernel<<<persistent_grid(kMaxRegions, 8), 256, 0, s>>>(n, state, scratch);
+  select_resolve_candidates_kernel<<<persistent_grid(kMaxRegions, 8), 256, 0, s>>>(n, state, scratch, mask);
 #define SFR_APPLY(M)                                                                                     \
   do {                                                                                                   \
     select_tie_count_kernel<M><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch);             \
     select_tie_block_sum_kernel<<<sum_grid, 256, 0, s>>>(nchunks, state, scratch);                       \
     select_tie_block_scan_kernel<<<1, 1024, 0, s>>>(nchunks, state, tie_base, scratch);                  \
     select_apply_kernel<M><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch, mask);           \
-    select_apply_stream_kernel<M><<<sgrid, kApplyThreads, 0, s>>>(a, b, eps, n, state, mask);            \
+    select_apply_stream_kernel<M><<<sgrid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch, mask);   \
   } while (0)
   if (key_mode == SFR_KEY_ABS) SFR_APPLY(SFR_KEY_ABS);
   else if (key_mode == SFR_KEY_RATIO) SFR_APPLY(SFR_KEY_RATIO);

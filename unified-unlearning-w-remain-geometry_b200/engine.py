@@ -64,6 +64,7 @@ class HotPath:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.zero_count = torch.zeros(capi.MAX_THRESHOLDS, dtype=torch.int64, device=self.device)
         self._select = None
+        self.select_two_pass = True    # False: pass 1 without the provisional mask, apply streams the vector again
         # replay-safe mode (CUDA graphs): the optimizer step counter lives on the device
         self.step_dev: Optional[torch.Tensor] = None
         # device scratch for the prep kernel of the fused update (step-dependent scalars, clip coefficient)
@@ -189,7 +190,8 @@ class HotPath:
         capi.select_hist(values, other, mode, 0, state, bins, None, eps)
         self.reduce_bins_(bins, capi.SELECT_BINS0)
         capi.select_scan(0, state, bins)
-        capi.select_hist(values, other, mode, 1, state, bins, scratch, eps)
+        # pass 1 also leaves the provisional mask, so apply only has to resolve the staged candidates
+        capi.select_hist(values, other, mode, 1, state, bins, scratch, eps, mask=mask if self.select_two_pass else None)
         local_bins = self.keep_local_bins_(bins)
         self.reduce_bins_(bins, capi.SELECT_BINS1)
         capi.select_scan(1, state, bins)

@@ -37,15 +37,19 @@ def _cpu(flat: torch.Tensor) -> torch.Tensor:
 def flat_to_dict(layout: FlatLayout, flat: torch.Tensor, *, all_names: Optional[Sequence[str]] = None,
                  prefix: str = "", dtype: Optional[torch.dtype] = None) -> Dict[str, object]:
     """name -> CPU tensor of the parameter's shape, in `all_names` order; names that are not in the
-    layout (frozen parameters) get the reference's int `0` placeholder."""
+    layout (frozen parameters) get the reference's int `0` placeholder.  ONE device->host copy; the
+    per-name tensors are views of that host vector (torch.save writes the shared storage once — at SD
+    size a per-tensor clone would be another 3.4 GB of host memcpy per Fisher file)."""
     host = _cpu(flat)
     if dtype is not None:
         host = host.to(dtype)
+    if host.data_ptr() == flat.data_ptr():
+        host = host.clone()                  # flat already lived on the host: do not alias the caller's buffer
     out: Dict[str, object] = {}
     for name in (all_names if all_names is not None else layout.names):
         if name in layout:
             s = layout.segment(name)
-            out[prefix + name] = host[s.offset:s.offset + s.numel].clone().view(s.shape)
+            out[prefix + name] = host[s.offset:s.offset + s.numel].view(s.shape)
         else:
             out[prefix + name] = 0
     return out
@@ -53,16 +57,18 @@ def flat_to_dict(layout: FlatLayout, flat: torch.Tensor, *, all_names: Optional[
 
 def dict_to_flat(layout: FlatLayout, d: Dict[str, object], *, prefix: str = "", dtype=torch.float32,
                  device="cpu") -> torch.Tensor:
-    """Pack a reference-format dict into a flat vector (int-0 placeholders are skipped)."""
-    out = torch.zeros(layout.numel, dtype=dtype)
+    """Pack a reference-format dict into a flat vector on `device` (int-0 placeholders are skipped).
+    Every tensor is copied straight into its slice of the destination (dtype conversion included), without
+    a packed host intermediate."""
+    out = torch.zeros(layout.numel, dtype=dtype, device=device)
     for s in layout:
         v = d[prefix + s.name]
         if not torch.is_tensor(v):
             raise ValueError(f"{prefix + s.name}: placeholder {v!r} for a trainable parameter")
         if tuple(v.shape) != s.shape:
             raise ValueError(f"{prefix + s.name}: shape {tuple(v.shape)} != {s.shape}")
-        out[s.offset:s.offset + s.numel].copy_(v.reshape(-1).to(dtype))
-    return out.to(device)
+        out[s.offset:s.offset + s.numel].copy_(v.reshape(-1))
+    return out
 
 
 # ---- Fisher ----------------------------------------------------------------------------------------
