@@ -260,6 +260,17 @@ def test_ddpm_runner_dropin_against_whole_reference_methods(dev, tmp_path):
     assert rec["kinds"][0::2] == ["forget"] * len(gf)
     un.forget(len(gf), lambda i: inject(un.model, gf[i]), lambda i: inject(un.model, gr[i]))
     check_final(un, rec, 2 * len(gf))
+    # the same loop with the WHOLE iteration captured in a CUDA graph: static gradient buffers refilled per replay
+    un = fresh()
+    un.load_mask(path)
+    gf_s, gr_s = torch.zeros_like(gf[0], device=dev), torch.zeros_like(gr[0], device=dev)
+
+    def refill(i):
+        gf_s.copy_(gf[i], non_blocking=False)
+        gr_s.copy_(gr[i], non_blocking=False)
+
+    un.forget(len(gf), lambda i: inject(un.model, gf_s), lambda i: inject(un.model, gr_s), cuda_graph=True, refill=refill)
+    check_final(un, rec, 2 * len(gf))
     # --mode saliency_unlearn: joint loss, clip BEFORE the int64 top-k mask
     un, rec = fresh(), fx["salun"]
     un.load_mask(unflat(fx["topk"]["mask"], pnames, fx["shapes"]))

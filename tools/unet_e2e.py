@@ -89,6 +89,10 @@ class Family:
         z = torch.randn(n, 4, 64, 64, device=dev, generator=g)
         return z, torch.randint(0, 1000, (n,), device=dev, generator=g), torch.randn(n, 4, 64, 64, device=dev, generator=g)
 
+    def draw(self, forget):
+        """One synthetic batch (fresh tensors) for the forget / remain losses."""
+        return self._ddpm_batch(forget) if self.name == "ddpm" else self._sd_batch()
+
     def fisher_loss(self, forget):
         if self.name == "ddpm":
             from ddpm_unet import eps_loss
@@ -99,14 +103,15 @@ class Family:
         ctx = (self.ctx_forget if forget else self.ctx_pseudo).expand(self.bs, -1, -1)
         return guided_eps_loss(self.model, z, t, ctx, self.ctx_null.expand(self.bs, -1, -1), e, self.ac, cond_scale=7.5)
 
-    def forget_loss(self):
+    def forget_loss(self, batch=None):
+        batch = self.draw(True) if batch is None else batch
         if self.name == "ddpm":                       # adaga: -adaptive_loss(...), DDPM/functions/losses.py:49-69
             from ddpm_unet import eps_loss
-            x, t, c, e = self._ddpm_batch(True)
+            x, t, c, e = batch
             per = eps_loss(self.model, x, t, c, e, self.ac, mode="train", keepdim=True)
             coef = 1 / (torch.pow(per.detach().clone(), 0.5) + 1e-8)
             return -((coef / coef.sum()) * per * self.bs).mean(dim=0)
-        z, t, e = self._sd_batch()                    # nsfw_removal.py:141-155
+        z, t, e = batch                               # nsfw_removal.py:141-155
         a = self.ac.index_select(0, t).view(-1, 1, 1, 1)
         zt = a.sqrt() * z + (1 - a).sqrt() * e
         out = self.model(zt, t, self.ctx_forget.expand(self.bs, -1, -1))
@@ -114,13 +119,14 @@ class Family:
             pseudo = self.model(zt, t, self.ctx_pseudo.expand(self.bs, -1, -1))
         return torch.nn.functional.mse_loss(out, pseudo)
 
-    def remain_loss(self):
+    def remain_loss(self, batch=None):
+        batch = self.draw(False) if batch is None else batch
         if self.name == "ddpm":
             from ddpm_unet import eps_loss
-            x, t, c, e = self._ddpm_batch(False)
+            x, t, c, e = batch
             return eps_loss(self.model, x, t, c, e, self.ac, mode="train")
         from sd_unet import eps_mse_loss
-        z, t, e = self._sd_batch()
+        z, t, e = batch
         return eps_mse_loss(self.model, z, t, self.ctx_pseudo.expand(self.bs, -1, -1), e, self.ac)
 
 
@@ -210,7 +216,7 @@ def stock(fam: Family, n_fisher, n_iters, tmp):
     return t_f, t_m, t_l, mask
 
 
-def ours(fam: Family, n_fisher, n_iters, tmp):
+def ours(fam: Family, n_fisher, n_iters, tmp, cuda_graph=False):
     from sfron_b200.methods.diffusion import DiffusionUnlearner
     from sfron_b200.methods.masks import generate_fisher_mask
     un = DiffusionUnlearner(fam.model, "ddpm" if fam.name == "ddpm" else "sd", lr=fam.lr)
@@ -229,13 +235,29 @@ def ours(fam: Family, n_fisher, n_iters, tmp):
     def loop_stage(n_steps):
         un.load_mask(os.path.join(tmp, fam.fisher_names[2].format(th="1.0")))
         fam.reseed(3)
-        un.forget(n_steps, lambda i: fam.forget_loss(), lambda i: fam.remain_loss(), forget_alpha=fam.forget_alpha,
-                  decay_forget_alpha=fam.decay)
+        if not cuda_graph:
+            un.forget(n_steps, lambda i: fam.forget_loss(), lambda i: fam.remain_loss(), forget_alpha=fam.forget_alpha,
+                      decay_forget_alpha=fam.decay)
+            return
+        # whole iteration in one CUDA graph: the batches live in static tensors, refilled before every replay
+        fb, rb = fam.draw(True), fam.draw(False)
+
+        def refill(step):
+            for dst, src in zip(fb, fam.draw(True)):
+                dst.copy_(src)
+            for dst, src in zip(rb, fam.draw(False)):
+                dst.copy_(src)
+
+        un.forget(n_steps, lambda i: fam.forget_loss(fb), lambda i: fam.remain_loss(rb), forget_alpha=fam.forget_alpha,
+                  decay_forget_alpha=fam.decay, cuda_graph=True, refill=refill)
 
     t_f, _ = _timed(fisher_stage)
     t_m, path = _timed(mask_stage)
     _timed(lambda: loop_stage(2))
     t_l, _ = _timed(lambda: loop_stage(n_iters))
+    if cuda_graph:
+        fam.graph_capture_s = un.graph_capture_s
+        t_l -= un.graph_capture_s               # one-off capture reported separately
     return t_f, t_m, t_l, torch.load(path, weights_only=False)
 
 
@@ -246,6 +268,8 @@ def main():
     ap.add_argument("--iters", type=int, default=None, help="forget-loop iterations (config 2: 50)")
     ap.add_argument("--fisher-batches", type=int, default=None, help="batches per Fisher (forget and remain each)")
     ap.add_argument("--batch-size", type=int, default=None)
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="ours arm: DiffusionUnlearner.forget(cuda_graph=True) — the whole iteration captured once and replayed")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -263,9 +287,15 @@ def main():
         res["params"] = fam.n
         warmup(fam)
         with tempfile.TemporaryDirectory() as tmp:
-            t_f, t_m, t_l, masks[name] = fn(fam, n_fisher, iters, tmp)
+            if name == "ours":
+                t_f, t_m, t_l, masks[name] = ours(fam, n_fisher, iters, tmp, cuda_graph=args.cuda_graph)
+            else:
+                t_f, t_m, t_l, masks[name] = stock(fam, n_fisher, iters, tmp)
         res[name] = {"fisher_s": round(t_f, 4), "fisher_batches_per_s": round(2 * n_fisher / t_f, 3),
                      "mask_s": round(t_m, 4), "loop_s": round(t_l, 4), "loop_steps_per_s": round(iters / t_l, 3)}
+        if name == "ours" and args.cuda_graph:
+            res[name]["cuda_graph"] = True
+            res[name]["graph_capture_s"] = round(fam.graph_capture_s, 4)
         del fam
         torch.cuda.empty_cache()
     if len(masks) == 2:

@@ -121,6 +121,8 @@ select_hist0_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
 //                                 only the first ceil(nchunks / kScanBlock) words are used
 //   header (kCandHeader words):   [0] overflow flag, [1] number of regions, [2] region capacity,
 //                                 [3] 1 if pass 1 also wrote the provisional mask, [4] that mask's address,
+//                                 [5] number of chunks listed as holding a tie, [6] 1 if that list overflowed
+//                                 (the list lives in the unused tail of the second scratch region),
 //                                 [8 + r] entries staged in region r
 //   candidate regions             cand_cap words: (flat index << 16) | key[15:0]
 constexpr int64_t kChunkElems = 8192;       // == kChunk below (kApplyThreads * 4 * kChunkVecs)
@@ -364,6 +366,12 @@ __device__ __forceinline__ bool ties_need_order(const sfr_select_state* s) {
   return !s->select_none && !s->select_all && s->tie_budget != s->count_eq;
 }
 
+// Chunks that hold a threshold-equal key, listed by the candidate walk so that the ordered apply visits
+// only those (a CTA polling 70 per-chunk counters one after the other is a 50 us chain of dependent L2 loads).
+// The list occupies scratch[nchunks + nblocks, 2 * nchunks): everything the block bases do not use.
+__host__ __device__ inline int64_t tie_list_offset(int64_t nchunks) { return nchunks + (nchunks + 4095) / 4096; }
+__host__ __device__ inline int64_t tie_list_cap(int64_t nchunks) { return 2 * nchunks - tie_list_offset(nchunks); }
+
 // The candidate list is complete (no region overflowed) and pass 1 left the provisional mask in THIS
 // mask buffer: only the staged candidates (and the chunks that hold an ordered tie) remain to be written.
 __device__ __forceinline__ bool provisional_ok(const unsigned long long* hdr, const uint8_t* mask) {
@@ -442,11 +450,13 @@ select_resolve_candidates_kernel(int64_t n, const sfr_select_state* __restrict__
                                  unsigned long long* __restrict__ scratch, uint8_t* __restrict__ mask) {
   if (state->select_none || state->select_all) return;
   const int64_t nchunks = (n + kChunk - 1) / kChunk;
-  const unsigned long long* hdr = scratch + 2 * nchunks;
+  unsigned long long* hdr = scratch + 2 * nchunks;
   if (hdr[0] != 0ull) return;  // overflow: the streaming kernels count and write instead
   const bool order = ties_need_order(state);
   const bool write = provisional_ok(hdr, mask);
   if (!order && !write) return;
+  unsigned long long* tie_list = scratch + tie_list_offset(nchunks);
+  const unsigned long long list_cap = (unsigned long long)tie_list_cap(nchunks);
   const unsigned int thr16 = state->thr_key & 0xffffu;
   const int regions = (int)hdr[1];
   const unsigned long long cap = hdr[2];
@@ -457,8 +467,16 @@ select_resolve_candidates_kernel(int64_t n, const sfr_select_state* __restrict__
       const unsigned long long e = region[i];
       const unsigned int low = (unsigned int)(e & 0xffffull);
       if (low == thr16) {
-        if (order) atomicAdd(scratch + (e >> 16) / kChunk, 1ull);
-        else mask[e >> 16] = 1;            // write is true here
+        if (order) {
+          const unsigned long long chunk = (e >> 16) / kChunk;
+          if (atomicAdd(scratch + chunk, 1ull) == 0ull) {      // first tie seen in this chunk: list it
+            const unsigned long long pos = atomicAdd(hdr + 5, 1ull);
+            if (pos < list_cap) tie_list[pos] = chunk;
+            else hdr[6] = 1ull;
+          }
+        } else {
+          mask[e >> 16] = 1;               // write is true here
+        }
       } else if (write && low > thr16) {
         mask[e >> 16] = 1;
       }
@@ -593,10 +611,16 @@ select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
   const unsigned long long budget = state->tie_budget;
   const int64_t nchunks = (n + kChunk - 1) / kChunk;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // provisional mask in place: only the chunks that hold a threshold-equal key are rewritten
-  const bool only_tie_chunks = provisional_ok(scratch + 2 * nchunks, mask);
+  // provisional mask in place: only the chunks that hold a threshold-equal key are rewritten, taken
+  // from the list the candidate walk left (or, if that overflowed, found by polling every counter)
+  const unsigned long long* hdr = scratch + 2 * nchunks;
+  const bool only_tie_chunks = provisional_ok(hdr, mask);
+  const bool listed = only_tie_chunks && hdr[6] == 0ull;
+  const unsigned long long* tie_list = scratch + tie_list_offset(nchunks);
+  const int64_t visits = listed ? (int64_t)hdr[5] : nchunks;
 
-  for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+  for (int64_t visit = blockIdx.x; visit < visits; visit += gridDim.x) {
+    const int64_t c = listed ? (int64_t)tie_list[visit] : visit;
     const int64_t base = c * kChunk;
     const unsigned long long chunk_ties = scratch[c];        // uniform over the CTA
     if (chunk_ties == 0 && only_tie_chunks) continue;
@@ -819,6 +843,7 @@ extern "C" int sfr_select_apply(const float* a, const float* b, int key_mode, fl
   const int sgrid = persistent_grid(((n >> 2) + stile - 1) / stile, 4);
   // the per-chunk counters are accumulated into: clear them here so that apply is idempotent
   cudaMemsetAsync(scratch, 0, (size_t)nchunks * sizeof(unsigned long long), s);
+  cudaMemsetAsync(scratch + 2 * nchunks + 5, 0, 2 * sizeof(unsigned long long), s);   // tie-chunk list: count, overflow
   select_resolve_candidates_kernel<<<persistent_grid(kMaxRegions, 8), 256, 0, s>>>(n, state, scratch, mask);
 #define SFR_APPLY(M)                                                                                     \
   do {                                                                                                   \

@@ -34,6 +34,15 @@ def _cpu(flat: torch.Tensor) -> torch.Tensor:
     return flat.detach().to("cpu")
 
 
+def load_file(path):
+    """torch.load of a reference-format dict, memory-mapped when the file allows it: the tensors are then
+    copied to the device straight from the page cache instead of through a private host copy of the file."""
+    try:
+        return torch.load(path, weights_only=False, mmap=True)
+    except (RuntimeError, ValueError):          # legacy (non-zip) files cannot be mapped
+        return torch.load(path, weights_only=False)
+
+
 def flat_to_dict(layout: FlatLayout, flat: torch.Tensor, *, all_names: Optional[Sequence[str]] = None,
                  prefix: str = "", dtype: Optional[torch.dtype] = None) -> Dict[str, object]:
     """name -> CPU tensor of the parameter's shape, in `all_names` order; names that are not in the
@@ -77,7 +86,7 @@ def save_fisher(path: str, layout: FlatLayout, flat: torch.Tensor, *, all_names=
 
 
 def load_fisher(path: str, layout: FlatLayout, *, prefix: str = "", device="cpu") -> torch.Tensor:
-    return dict_to_flat(layout, torch.load(path, weights_only=False), prefix=prefix, device=device)
+    return dict_to_flat(layout, load_file(path), prefix=prefix, device=device)
 
 
 def save_fim_pickle(path: str, layout: FlatLayout, flat: torch.Tensor, *, prefix: str = "") -> None:
@@ -106,7 +115,7 @@ def topk_mask_to_dict(layout: FlatLayout, mask_u8: torch.Tensor, *, all_names=No
 
 def load_mask(path_or_dict, layout: FlatLayout, *, prefix: str = "", device="cpu") -> torch.Tensor:
     """Any reference mask file (bool or int64) -> flat uint8 0/1."""
-    d = torch.load(path_or_dict, weights_only=False) if isinstance(path_or_dict, (str, os.PathLike)) else path_or_dict
+    d = load_file(path_or_dict) if isinstance(path_or_dict, (str, os.PathLike)) else path_or_dict
     return dict_to_flat(layout, d, prefix=prefix, dtype=torch.uint8, device=device)
 
 

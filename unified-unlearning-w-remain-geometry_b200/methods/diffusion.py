@@ -170,11 +170,20 @@ class DiffusionUnlearner:
     # ---- forget loops ----------------------------------------------------------------------------------
     def forget(self, n_iters: int, forget_loss_fn: LossFn, remain_loss_fn: LossFn, *, use_mask: bool = True,
                forget_alpha: float = 1.0, remain_alpha: float = 1.0, decay_forget_alpha: bool = False,
-               mask_order: str = "mask_then_clip", log_every: int = 0) -> None:
+               mask_order: str = "mask_then_clip", log_every: int = 0, cuda_graph: bool = False,
+               refill: Optional[Callable[[int], None]] = None) -> None:
         """method "ron": forget step (mask, clip, step) then remain step (clip?, step) then EMA, every
         iteration (runners/diffusion.py:1075-1180; DiT/forget.py:256-322; nsfw_removal.py:108-173).
-        The closures return the UNWEIGHTED losses (-loss for gradient ascent)."""
+        The closures return the UNWEIGHTED losses (-loss for gradient ascent).
+
+        cuda_graph=True captures ONE whole iteration — both PyTorch forward/backward passes and the hot-path
+        kernels — in a CUDA graph and replays it n_iters times (the small-batch loops are launch-bound).
+        The closures must then read their batch from STATIC device tensors and `refill(step)` is called
+        before each replay to copy the next batch into them; alpha_t reaches the graph as a device scalar."""
         mhp, cfg = self.mhp, self.cfg
+        if cuda_graph:
+            return self._forget_graphed(n_iters, forget_loss_fn, remain_loss_fn, use_mask, forget_alpha,
+                                        remain_alpha, decay_forget_alpha, mask_order, refill)
         mhp.zero_grad()
         self.model.train()
         for step in range(n_iters):
@@ -185,6 +194,65 @@ class DiffusionUnlearner:
             mhp.remain_step(max_norm=cfg.clip_remain, ema=True)
             if log_every and (step + 1) % log_every == 0:
                 print(f"step:{step:04d} forget a:{alpha:.8f}")
+
+    def _forget_graphed(self, n_iters, forget_loss_fn, remain_loss_fn, use_mask, forget_alpha, remain_alpha,
+                        decay_forget_alpha, mask_order, refill) -> None:
+        mhp, cfg, hp, flat = self.mhp, self.cfg, self.mhp.hp, self.mhp.flat
+        if not flat.grads_as_views:
+            raise RuntimeError("cuda_graph=True needs view-gradients (FlatParams(grads_as_views=True))")
+        import time
+        t_capture = time.perf_counter()
+        hp.enable_graph_replay()                      # optimizer step counter on the device; buffers allocated
+        self.model.train()
+        alpha_dev = torch.zeros((), dtype=torch.float32, device=flat.device)
+
+        def body():
+            (alpha_dev * forget_loss_fn(0)).backward()
+            mhp.forget_step(use_mask=use_mask, max_norm=cfg.clip_forget, mask_order=mask_order)
+            (remain_alpha * remain_loss_fn(0)).backward()
+            mhp.remain_step(max_norm=cfg.clip_remain, ema=True)
+
+        # One eager iteration on a side stream (cuDNN / cuBLAS pick their algorithms and workspaces outside the
+        # capture), with the state it advances put back afterwards: the run makes exactly n_iters steps.
+        roles = [r for r in ("m", "v", "slow") if hp.has(r)]
+        saved = {r: hp.buffer(r).clone() for r in roles}
+        saved_p = flat.p.clone()
+        saved_w = None if flat.p_work is None else flat.p_work.clone()
+        saved_frozen = None if mhp.frozen_slow is None else mhp.frozen_slow.clone()
+        saved_step, saved_count = hp.step_dev.clone(), hp.step_count
+        if refill is not None:
+            refill(0)
+        alpha_dev.fill_(cosine_lr_scheduler(forget_alpha, 0, n_iters) if decay_forget_alpha else forget_alpha)
+        mhp.zero_grad()
+        side = torch.cuda.Stream(device=flat.device)
+        side.wait_stream(torch.cuda.current_stream(flat.device))
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream(flat.device).wait_stream(side)
+        for r in roles:
+            hp.buffer(r).copy_(saved[r])
+        flat.p.copy_(saved_p)
+        if saved_w is not None:
+            flat.p_work.copy_(saved_w)
+        if saved_frozen is not None:
+            mhp.frozen_slow.copy_(saved_frozen)
+        hp.step_dev.copy_(saved_step)
+        hp.step_count = saved_count
+        del saved, saved_p, saved_w, saved_frozen
+        mhp.zero_grad()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+        # capture records, it does not execute: state is untouched, but the host-side counter moved
+        hp.step_count = saved_count
+        torch.cuda.synchronize(flat.device)
+        self.graph_capture_s = time.perf_counter() - t_capture     # one-off cost, reported by the e2e tools
+        for step in range(n_iters):
+            alpha_dev.fill_(cosine_lr_scheduler(forget_alpha, step, n_iters) if decay_forget_alpha else forget_alpha)
+            if refill is not None:
+                refill(step)
+            graph.replay()
+        hp.step_count = saved_count + 2 * n_iters
 
     def saliency_unlearn(self, n_iters: int, joint_loss_fn: LossFn, *, use_mask: bool = True,
                          log_every: int = 0) -> None:

@@ -50,8 +50,8 @@ def ratio_masks_from_fishers(forget_fisher: Dict[str, object], remain_fisher: Di
 
 def generate_fisher_mask(ckpt_folder: str, threshold: float = 1.0, *, forget_name="forget_fisher.pt",
                          remain_name="remain_fisher.pt", out_fmt="fisher_{th}.pt", device="cuda") -> str:
-    forget_fisher = torch.load(os.path.join(ckpt_folder, forget_name), weights_only=False)
-    remain_fisher = torch.load(os.path.join(ckpt_folder, remain_name), weights_only=False)
+    forget_fisher = formats.load_file(os.path.join(ckpt_folder, forget_name))
+    remain_fisher = formats.load_file(os.path.join(ckpt_folder, remain_name))
     (mask,) = ratio_masks_from_fishers(forget_fisher, remain_fisher, [threshold], device)
     path = os.path.join(ckpt_folder, out_fmt.format(th=formats.threshold_tag(threshold)))
     torch.save(mask, path)
@@ -63,8 +63,8 @@ def generate_mask_dit(mask_path: str, forget_class: Sequence[int], thresholds: S
     written = []
     for cls in forget_class:
         folder = os.path.join(mask_path, str(cls))
-        forget_fisher = torch.load(os.path.join(folder, "forget_fisher.pt"), weights_only=False)
-        remain_fisher = torch.load(os.path.join(folder, "remain_fisher.pt"), weights_only=False)
+        forget_fisher = formats.load_file(os.path.join(folder, "forget_fisher.pt"))
+        remain_fisher = formats.load_file(os.path.join(folder, "remain_fisher.pt"))
         for name, v in forget_fisher.items():
             if not torch.is_tensor(v):
                 print(f"{name} {v}")                      # the reference's except-branch print
