@@ -141,3 +141,25 @@ def test_scan_from_top_matches_bruteforce(data):
     else:
         assert above < want <= above + counts[b] and above == sum(counts[b + 1:])
     assert tie_bases([3, 0, 2]) == [0, 3, 3]
+
+
+def test_format_converters_single_copy_semantics(tmp_path):
+    """flat_to_dict hands out views of ONE host copy (never of the caller's buffer); a saved file reloads —
+    memory-mapped — into the same dict; dict_to_flat packs bool / int64 / fp32 entries straight into the target."""
+    layout = sfr.FlatLayout([("a", (2, 3)), ("b", (5,)), ("c", ())])
+    flat = torch.arange(12, dtype=torch.float32)
+    d = formats.flat_to_dict(layout, flat, all_names=["frozen", "a", "b", "c"], prefix="module.")
+    assert list(d) == ["module.frozen", "module.a", "module.b", "module.c"] and d["module.frozen"] == 0
+    d["module.a"][0, 0] = 99.0
+    assert flat[0] == 0.0                                           # the caller's vector is not aliased
+    assert d["module.a"].untyped_storage().data_ptr() == d["module.b"].untyped_storage().data_ptr()
+    path = tmp_path / "forget_fisher.pt"
+    torch.save(d, path)
+    back = formats.load_file(str(path))
+    assert back["module.frozen"] == 0 and torch.equal(back["module.b"], d["module.b"])
+    assert torch.equal(formats.load_fisher(str(path), layout, prefix="module."), torch.cat([d[k].reshape(-1) for k in list(d)[1:]]))
+    bits = (flat > 3).to(torch.uint8)
+    for to_dict, dtype in ((formats.ratio_mask_to_dict, torch.bool), (formats.topk_mask_to_dict, torch.int64)):
+        m = to_dict(layout, bits)
+        assert all(t.dtype == dtype for t in m.values())
+        assert torch.equal(formats.load_mask(m, layout), bits)
