@@ -141,6 +141,9 @@ SFR_API int sfr_ratio_mask_multi(const float* ff, const float* rf, int64_t n,
 #define SFR_KEY_ABSDIFF 2 /* x = a[i] - b[i]  (proximal gradient: |theta - theta0|) */
 #define SFR_SELECT_BINS0 32768 /* key bits [30:16] */
 #define SFR_SELECT_BINS1 65536 /* key bits [15:0]  */
+/* u64 words every bins_dev buffer must hold: the histogram bins plus the scan's per-CTA partial sums and
+ * ticket counter.  Only bins[0 .. SFR_SELECT_BINS0 / BINS1) take part in the multi-GPU all-reduce. */
+#define SFR_SELECT_BINS_ALLOC (65536 + 128)
 
 typedef struct sfr_select_state {
   unsigned long long k;          /* in: number of elements to select (global)        */

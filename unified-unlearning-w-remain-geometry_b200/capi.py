@@ -24,6 +24,7 @@ OK, ERR_NULL, ERR_ALIGN, ERR_ARG, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 F32, BF16 = 0, 1
 KEY_ABS, KEY_RATIO, KEY_ABSDIFF = 0, 1, 2
 SELECT_BINS0, SELECT_BINS1 = 32768, 65536
+SELECT_BINS_ALLOC = 65536 + 128         # u64 words of a bins buffer (histogram + the scan's partials / ticket)
 MAX_THRESHOLDS = 8
 OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2
 EMA_NONE, EMA_DDPM, EMA_DIT, EMA_SLOWFAST = 0, 1, 2, 3
@@ -213,7 +214,7 @@ def ratio_mask_multi(ff: torch.Tensor, rf: torch.Tensor, thresholds: Sequence[fl
 
 # ---- K2b -----------------------------------------------------------------------------------
 def select_init(state: torch.Tensor, bins: torch.Tensor, k: int) -> None:
-    if state.numel() * state.element_size() < SELECT_STATE_BYTES or bins.numel() < SELECT_BINS1:
+    if state.numel() * state.element_size() < SELECT_STATE_BYTES or bins.numel() < SELECT_BINS_ALLOC:
         raise SfrError(ERR_ARG, "select_init", "state / bins buffers too small")
     _check(load().sfr_select_init(_ptr(state, torch.int64, "state"), _ptr(bins, torch.int64, "bins"),
                                   int(k), _stream()), "sfr_select_init")

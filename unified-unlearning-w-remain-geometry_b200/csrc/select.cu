@@ -245,30 +245,32 @@ select_hist1_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
   }
 }
 
-// ---- scans (one CTA) -----------------------------------------------------------------------
-constexpr int kScanThreads = 1024;
+// ---- scans (multi-CTA, last CTA finishes) ------------------------------------------------------
+// Finds the largest bin B with  above(B) < want <= above(B) + bins[B]  (scanning from the top).
+// A single-CTA scan of 32 k / 64 k counters is a 29 / 48 us latency chain on one SM; here one CTA per
+// 1024 bins forms a partial sum, and the last CTA to arrive (ticket counter, __threadfence) scans the
+// <= 64 partials, then the 1024 bins of the block that holds the crossing.  Partials and the ticket
+// live in the tail of the bins buffer: bins[SFR_SELECT_BINS1 .. SFR_SELECT_BINS_ALLOC).
+constexpr int kScanThreads = 256;
+constexpr int kScanCtaBins = 1024;                       // bins per CTA = 4 per thread
+constexpr int kScanMaxCtas = SFR_SELECT_BINS1 / kScanCtaBins;   // 64
+static_assert(SFR_SELECT_BINS_ALLOC >= SFR_SELECT_BINS1 + kScanMaxCtas + 1, "bins tail too small");
 
-// Finds the largest bin B with  above(B) < want <= above(B) + bins[B], scanning from the top.
-// Returns (B, above(B)) to every thread through shared memory; B = -1 if want > total.
-// Thread t owns kPer consecutive bins (descending); all kPer loads are issued before the first
-// add, thread sums are scanned with warp shuffles (one barrier pair for the 32 warp totals).
-// (Keeping the kPer counters in registers would spill at 1024 threads; the one thread that holds
-// the crossing re-reads its bins instead.)
-template <int NBINS>
-__device__ void find_bin_from_top(const unsigned long long* __restrict__ bins,
-                                  unsigned long long want, int* out_bin,
-                                  unsigned long long* out_above, unsigned long long* out_total) {
-  constexpr int kPer = NBINS / kScanThreads;
-  __shared__ unsigned long long warp_tot[32];
-  __shared__ int s_bin;
-  __shared__ unsigned long long s_above, s_total;
+// Block-wide search inside `count` descending values held one per thread-slot: thread t owns
+// values v[0..PER) = positions t*PER .. t*PER+PER-1 of the descending order.  Returns through shared
+// memory the position (0-based from the top) of the crossing and the sum above it; -1 if want > total.
+template <int PER>
+__device__ void find_crossing(const unsigned long long (&v)[PER], unsigned long long want,
+                              unsigned long long carry_above, int* out_pos, unsigned long long* out_above) {
+  __shared__ unsigned long long warp_tot[kScanThreads / 32];
+  __shared__ int s_pos;
+  __shared__ unsigned long long s_above;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int hi = NBINS - 1 - (int)threadIdx.x * kPer;
   unsigned long long mine = 0;
-#pragma unroll 8
-  for (int j = 0; j < kPer; ++j) mine += bins[hi - j];  // 8 independent loads in flight
+#pragma unroll
+  for (int j = 0; j < PER; ++j) mine += v[j];
   if (threadIdx.x == 0) {
-    s_bin = -1;
+    s_pos = -1;
     s_above = 0;
   }
   unsigned long long incl = mine;
@@ -279,73 +281,100 @@ __device__ void find_bin_from_top(const unsigned long long* __restrict__ bins,
   }
   if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
-  if (warp == 0) {
-    unsigned long long w = warp_tot[lane], wi = w;
+  unsigned long long before = carry_above;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long up = __shfl_up_sync(kFullMask, wi, o);
-      if (lane >= o) wi += up;
-    }
-    warp_tot[lane] = wi - w;  // exclusive prefix of the warp totals
-    if (lane == 31) s_total = wi;
-  }
-  __syncthreads();
-  const unsigned long long excl = warp_tot[warp] + (incl - mine);
+  for (int w = 0; w < kScanThreads / 32; ++w)
+    if (w < warp) before += warp_tot[w];
+  const unsigned long long excl = before + (incl - mine);
   if (want > excl && want <= excl + mine) {  // exactly one thread
-    // re-read this thread's bins (L2-resident) with independent loads; no dependent branches
-    unsigned long long above = excl, found_above = 0;
+    unsigned long long above = excl;
     int found = -1;
-#pragma unroll 8
-    for (int j = 0; j < kPer; ++j) {
-      const unsigned long long c = bins[hi - j];
-      if (found < 0 && want <= above + c) {
-        found = hi - j;
+    unsigned long long found_above = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      if (found < 0 && want <= above + v[j]) {
+        found = (int)threadIdx.x * PER + j;
         found_above = above;
       }
-      above += c;
+      above += v[j];
     }
-    s_bin = found;
+    s_pos = found;
     s_above = found_above;
   }
   __syncthreads();
-  *out_bin = s_bin;
+  *out_pos = s_pos;
   *out_above = s_above;
-  *out_total = s_total;
   __syncthreads();
 }
 
 __global__ void __launch_bounds__(kScanThreads, 1)
 select_scan_kernel(int pass, sfr_select_state* __restrict__ state,
                    unsigned long long* __restrict__ bins) {
-  int bin;
-  unsigned long long above, total;
-  if (pass == 0) {
-    const unsigned long long k = state->k;
-    find_bin_from_top<SFR_SELECT_BINS0>(bins, k, &bin, &above, &total);
+  constexpr int kPer = kScanCtaBins / kScanThreads;   // 4
+  unsigned long long* partial = bins + SFR_SELECT_BINS1;
+  unsigned long long* ticket = partial + kScanMaxCtas;
+  __shared__ unsigned long long red[32];
+  __shared__ bool s_last;
+  const int nctas = gridDim.x;                         // NBINS / kScanCtaBins
+  // partial sum of this CTA's 1024 bins
+  {
+    const unsigned long long* mine = bins + (int64_t)blockIdx.x * kScanCtaBins;
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) sum += mine[threadIdx.x + j * kScanThreads];
+    sum = block_sum<unsigned long long>(sum, red);
     if (threadIdx.x == 0) {
+      partial[blockIdx.x] = sum;
+      __threadfence();
+      s_last = atomicAdd(ticket, 1ull) == (unsigned long long)(nctas - 1);
+    }
+    __syncthreads();
+  }
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *ticket = 0ull;                // ready for the next scan
+
+  const bool skip = pass == 1 && (state->select_none || state->select_all);
+  const unsigned long long want = pass == 0 ? state->k : state->k_in_bin;
+  int bin = -1;
+  unsigned long long above = 0;
+  if (!skip) {
+    // level 1: the CTA partials, highest block first (thread t owns descending position t)
+    unsigned long long pv[1];
+    const int blk_of_t = nctas - 1 - (int)threadIdx.x;
+    pv[0] = ((int)threadIdx.x < nctas) ? __ldcg(partial + blk_of_t) : 0ull;
+    int pos;
+    unsigned long long above_blk;
+    find_crossing<1>(pv, want, 0ull, &pos, &above_blk);
+    if (pos >= 0) {
+      // level 2: the 1024 bins of that block, highest bin first (thread t owns descending positions 4t..4t+3)
+      const int blk = nctas - 1 - pos;
+      const unsigned long long* b = bins + (int64_t)blk * kScanCtaBins;
+      unsigned long long v[kPer];
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) v[j] = __ldcg(b + (kScanCtaBins - 1 - ((int)threadIdx.x * kPer + j)));
+      int p2;
+      unsigned long long above2;
+      find_crossing<kPer>(v, want, above_blk, &p2, &above2);
+      bin = blk * kScanCtaBins + (kScanCtaBins - 1 - p2);
+      above = above2;
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (pass == 0) {
+      const unsigned long long k = state->k;
       state->select_none = (k == 0);
       state->select_all = (k != 0 && bin < 0);  // k exceeds the element count
       state->prefix = bin < 0 ? 0u : (uint32_t)bin;
       state->k_in_bin = bin < 0 ? 0ull : k - above;
       state->count_gt = above;  // completed by scan 1
-    }
-  } else {
-    if (state->select_none || state->select_all) {
-      bin = -1;
-      above = total = 0;
-    } else {
-      find_bin_from_top<SFR_SELECT_BINS1>(bins, state->k_in_bin, &bin, &above, &total);
-    }
-    if (threadIdx.x == 0 && bin >= 0) {
+    } else if (bin >= 0) {
       state->thr_key = (state->prefix << 16) | (uint32_t)bin;
       state->count_gt += above;
-      state->count_eq = bins[bin];
+      state->count_eq = __ldcg(bins + bin);
       state->tie_budget = state->k_in_bin - above;
     }
   }
-  __syncthreads();
-  // leave the bins clean for the next pass / the next select
-  for (int i = threadIdx.x; i < SFR_SELECT_BINS1; i += kScanThreads) bins[i] = 0ull;
 }
 
 // ---- apply -----------------------------------------------------------------------------------
@@ -460,25 +489,42 @@ select_resolve_candidates_kernel(int64_t n, const sfr_select_state* __restrict__
   const unsigned int thr16 = state->thr_key & 0xffffu;
   const int regions = (int)hdr[1];
   const unsigned long long cap = hdr[2];
-  for (int r = blockIdx.x; r < regions; r += gridDim.x) {
+  // Work item = one quarter of one region; every thread issues its (up to) four list loads before it
+  // touches the mask: the walk is a latency chain otherwise (15 dependent rounds per CTA, 46 us at N3).
+  constexpr int kSplit = 4, kUnroll = 4;
+  const int items = regions * kSplit;
+  for (int w = blockIdx.x; w < items; w += gridDim.x) {
+    const int r = w / kSplit, part = w % kSplit;
     const unsigned long long* region = hdr + kCandHeader + (unsigned long long)r * cap;
     const unsigned int cnt = (unsigned int)hdr[8 + r];
-    for (unsigned int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const unsigned long long e = region[i];
-      const unsigned int low = (unsigned int)(e & 0xffffull);
-      if (low == thr16) {
-        if (order) {
-          const unsigned long long chunk = (e >> 16) / kChunk;
-          if (atomicAdd(scratch + chunk, 1ull) == 0ull) {      // first tie seen in this chunk: list it
-            const unsigned long long pos = atomicAdd(hdr + 5, 1ull);
-            if (pos < list_cap) tie_list[pos] = chunk;
-            else hdr[6] = 1ull;
+    const unsigned int per = (cnt + kSplit - 1) / kSplit;
+    const unsigned int lo = part * per;
+    const unsigned int hi = lo + per < cnt ? lo + per : cnt;
+    for (unsigned int i0 = lo + threadIdx.x; i0 < hi; i0 += blockDim.x * kUnroll) {
+      unsigned long long e[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const unsigned int i = i0 + u * blockDim.x;
+        e[u] = i < hi ? __ldcs(region + i) : ~0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        if (i0 + u * blockDim.x >= hi) continue;
+        const unsigned int low = (unsigned int)(e[u] & 0xffffull);
+        if (low == thr16) {
+          if (order) {
+            const unsigned long long chunk = (e[u] >> 16) / kChunk;
+            if (atomicAdd(scratch + chunk, 1ull) == 0ull) {      // first tie seen in this chunk: list it
+              const unsigned long long pos = atomicAdd(hdr + 5, 1ull);
+              if (pos < list_cap) tie_list[pos] = chunk;
+              else hdr[6] = 1ull;
+            }
+          } else {
+            mask[e[u] >> 16] = 1;            // write is true here
           }
-        } else {
-          mask[e >> 16] = 1;               // write is true here
+        } else if (write && low > thr16) {
+          mask[e[u] >> 16] = 1;
         }
-      } else if (write && low > thr16) {
-        mask[e >> 16] = 1;
       }
     }
   }
@@ -709,7 +755,7 @@ select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
 __global__ void select_init_kernel(sfr_select_state* state, unsigned long long* bins,
                                    unsigned long long k) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < SFR_SELECT_BINS1) bins[i] = 0ull;
+  if (i < SFR_SELECT_BINS_ALLOC) bins[i] = 0ull;
   if (i == 0) {
     sfr_select_state z{};
     z.k = k;
@@ -726,7 +772,7 @@ extern "C" int sfr_select_init(sfr_select_state* state, unsigned long long* bins
   SFR_REQUIRE_PTR(state);
   SFR_REQUIRE_PTR(bins);
   if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
-  select_init_kernel<<<SFR_SELECT_BINS1 / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(state, bins, k);
+  select_init_kernel<<<(SFR_SELECT_BINS_ALLOC + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(state, bins, k);
   SFR_LAUNCH_STATUS();
 }
 
@@ -807,7 +853,11 @@ extern "C" int sfr_select_scan(int pass, sfr_select_state* state, unsigned long 
   SFR_REQUIRE_PTR(state);
   SFR_REQUIRE_PTR(bins);
   if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
-  select_scan_kernel<<<1, kScanThreads, 0, static_cast<cudaStream_t>(stream)>>>(pass, state, bins);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nbins = pass == 0 ? SFR_SELECT_BINS0 : SFR_SELECT_BINS1;
+  select_scan_kernel<<<nbins / kScanCtaBins, kScanThreads, 0, s>>>(pass, state, bins);
+  // leave the bins clean for the next pass / the next select (the partials and the ticket stay as they are)
+  cudaMemsetAsync(bins, 0, (size_t)SFR_SELECT_BINS1 * sizeof(unsigned long long), s);
   SFR_LAUNCH_STATUS();
 }
 
@@ -844,7 +894,7 @@ extern "C" int sfr_select_apply(const float* a, const float* b, int key_mode, fl
   // the per-chunk counters are accumulated into: clear them here so that apply is idempotent
   cudaMemsetAsync(scratch, 0, (size_t)nchunks * sizeof(unsigned long long), s);
   cudaMemsetAsync(scratch + 2 * nchunks + 5, 0, 2 * sizeof(unsigned long long), s);   // tie-chunk list: count, overflow
-  select_resolve_candidates_kernel<<<persistent_grid(kMaxRegions, 8), 256, 0, s>>>(n, state, scratch, mask);
+  select_resolve_candidates_kernel<<<persistent_grid(kMaxRegions * 4, 8), 256, 0, s>>>(n, state, scratch, mask);
 #define SFR_APPLY(M)                                                                                     \
   do {                                                                                                   \
     select_tie_count_kernel<M><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch);             \

@@ -174,7 +174,7 @@ class HotPath:
     def _select_buffers(self):
         if self._select is None:
             state = torch.zeros(capi.SELECT_STATE_BYTES // 8, dtype=torch.int64, device=self.device)
-            bins = torch.zeros(capi.SELECT_BINS1, dtype=torch.int64, device=self.device)
+            bins = torch.zeros(capi.SELECT_BINS_ALLOC, dtype=torch.int64, device=self.device)
             scratch = torch.zeros(capi.select_scratch_elems(self.n), dtype=torch.int64, device=self.device)
             self._select = (state, bins, scratch)
         return self._select
