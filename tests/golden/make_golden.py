@@ -17,6 +17,10 @@ What is executed from the reference, unmodified:
     and sample_visualization (the 1000-step sampler after a snapshot) stubbed out
   * DiT/forget.py update_ema / cosine_lr_scheduler (function bodies extracted with `ast`,
     because the module imports diffusers at top level, absent here)
+  * DiT/generate_fisher.py main(), DiT/generate_mask.py main(), DiT/forget.py main() — the three scripts of
+    config 3 executed whole on a 1-block DiT built by the reference's own `DiT` class, with: stubs for the two
+    absent third-party imports (timm's PatchEmbed/Attention/Mlp, diffusers' AutoencoderKL), the one
+    `assert torch.cuda.is_available()` statement removed, synthetic datasets for get_unlearn_dataset
 The forget-loop bodies of DDPM/runners/diffusion.py:1122-1180 and DiT/forget.py:285-322 are
 inline in 1000-line methods that need datasets and full-size models; for those the script
 drives the reference's OWN optimizer / EMA objects with synthetic gradients in the order of
@@ -541,6 +545,201 @@ def dit_loop():
     print("wrote dit loop")
 
 
+# ------------------------------------------------------- DiT scripts, executed whole (config 3)
+def _install_dit_stubs():
+    """The two third-party imports of DiT/{models,forget,generate_fisher}.py that are absent here.
+    `timm.models.vision_transformer`: PatchEmbed / Attention / Mlp with timm's state-dict names
+    (proj | qkv, proj | fc1, fc2).  `diffusers.models.AutoencoderKL`: a parameter-free stand-in for the
+    frozen VAE encoder (8x average pooling to 4 channels)."""
+    class PatchEmbed(nn.Module):
+        def __init__(self, img_size, patch_size, in_chans, embed_dim, bias=True):
+            super().__init__()
+            self.num_patches = (img_size // patch_size) ** 2
+            self.patch_size = (patch_size, patch_size)
+            self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size, bias=bias)
+
+        def forward(self, x):
+            return self.proj(x).flatten(2).transpose(1, 2)
+
+    class Attention(nn.Module):
+        def __init__(self, dim, num_heads=8, qkv_bias=False, **kw):
+            super().__init__()
+            self.num_heads = num_heads
+            self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+            self.proj = nn.Linear(dim, dim)
+
+        def forward(self, x):
+            b, n, c = x.shape
+            q, k, v = self.qkv(x).reshape(b, n, 3, self.num_heads, c // self.num_heads).permute(2, 0, 3, 1, 4)
+            o = torch.nn.functional.scaled_dot_product_attention(q, k, v)
+            return self.proj(o.transpose(1, 2).reshape(b, n, c))
+
+    class Mlp(nn.Module):
+        def __init__(self, in_features, hidden_features, act_layer=nn.GELU, drop=0):
+            super().__init__()
+            self.fc1 = nn.Linear(in_features, hidden_features)
+            self.act = act_layer()
+            self.fc2 = nn.Linear(hidden_features, in_features)
+
+        def forward(self, x):
+            return self.fc2(self.act(self.fc1(x)))
+
+    timm = types.ModuleType("timm")
+    timm.models = types.ModuleType("timm.models")
+    vt = types.ModuleType("timm.models.vision_transformer")
+    vt.PatchEmbed, vt.Attention, vt.Mlp = PatchEmbed, Attention, Mlp
+    timm.models.vision_transformer = vt
+    sys.modules.update({"timm": timm, "timm.models": timm.models, "timm.models.vision_transformer": vt})
+
+    class _Dist:
+        def __init__(self, z):
+            self.z = z
+
+        def sample(self):
+            return self.z.clone()
+
+    class _Enc:
+        def __init__(self, z):
+            self.latent_dist = _Dist(z)
+
+    class AutoencoderKL(nn.Module):
+        @classmethod
+        def from_pretrained(cls, name):
+            return cls()
+
+        def encode(self, x):
+            z = torch.nn.functional.avg_pool2d(x, 8)
+            return _Enc(torch.cat([z, z.mean(1, keepdim=True)], dim=1))
+
+    diffusers = types.ModuleType("diffusers")
+    diffusers.models = types.ModuleType("diffusers.models")
+    diffusers.models.AutoencoderKL = AutoencoderKL
+    sys.modules.update({"diffusers": diffusers, "diffusers.models": diffusers.models})
+
+
+def _load_without_cuda_assert(path, name):
+    """Execute a reference script as a module with ONE statement removed: `assert torch.cuda.is_available()`
+    (DiT/forget.py:155, DiT/generate_fisher.py:135).  The next line of both scripts already falls back to the
+    CPU (`torch.device("cuda" if torch.cuda.is_available() else "cpu")`)."""
+    tree = ast.parse(open(path).read())
+
+    class Strip(ast.NodeTransformer):
+        removed = 0
+
+        def visit_Assert(self, node):
+            if "cuda.is_available" in ast.unparse(node.test):
+                Strip.removed += 1
+                return None
+            return node
+
+    tree = Strip().visit(tree)
+    assert Strip.removed == 1, path
+    mod = types.ModuleType(name)
+    mod.__file__ = path
+    exec(compile(ast.fix_missing_locations(tree), path, "exec"), mod.__dict__)
+    return mod
+
+
+def dit_scripts():
+    sys.path.insert(0, os.path.join(REF, "DiT"))
+    _install_dit_stubs()
+    import models as dit_models
+    built = []
+
+    def tiny(**kw):                       # 1 block, width 8, one 8x8 patch: 10,0xx parameters
+        m = dit_models.DiT(depth=1, hidden_size=8, patch_size=8, num_heads=2, **kw)
+        built.append(m)
+        return m
+    dit_models.DiT_models["DiT-tiny"] = tiny
+    gf_mod = _load_without_cuda_assert(os.path.join(REF, "DiT/generate_fisher.py"), "ref_dit_generate_fisher")
+    fg_mod = _load_without_cuda_assert(os.path.join(REF, "DiT/forget.py"), "ref_dit_forget")
+    gm_mod = importlib.import_module("generate_mask")
+
+    from torch.utils.data import TensorDataset
+    g = torch.Generator().manual_seed(41)
+    forget_ds = TensorDataset(torch.rand(5, 3, 64, 64, generator=g) * 2 - 1, torch.full((5,), 3))
+    remain_ds = TensorDataset(torch.rand(7, 3, 64, 64, generator=g) * 2 - 1, torch.randint(4, 10, (7,), generator=g))
+    for mod in (gf_mod, fg_mod):          # shims: synthetic data, no sampling grid
+        mod.get_unlearn_dataset = lambda data_path, forget_class, transform: (forget_ds, remain_ds)
+    fg_mod.sample_visualization = lambda *a, **k: None
+
+    class Recorder:
+        """raw gradient of the TRAINABLE parameters right after every backward (pos_embed is frozen)."""
+        def __init__(self):
+            self.records, self._orig = [], torch.Tensor.backward
+
+        def __enter__(self):
+            rec = self
+
+            def backward(t, *a, **k):
+                out = rec._orig(t, *a, **k)
+                rec.records.append(flat([p.grad if p.grad is not None else torch.zeros_like(p)
+                                         for p in built[-1].parameters() if p.requires_grad]))
+                return out
+            torch.Tensor.backward = backward
+            return self
+
+        def __exit__(self, *exc):
+            torch.Tensor.backward = self._orig
+
+    n_fisher, n_iters = 3, 4
+    with tempfile.TemporaryDirectory() as tmp:
+        # a randomly initialised checkpoint: the constructor zero-initialises adaLN / final layers (DiT/models.py)
+        torch.manual_seed(40)
+        init = tiny(input_size=8, num_classes=10)
+        with torch.no_grad():
+            for p in init.parameters():
+                if p.requires_grad and not p.any():
+                    p.normal_(std=0.02)
+        ckpt = os.path.join(tmp, "init.pt")
+        torch.save(init.state_dict(), ckpt)
+        pnames = ["module." + n for n, _ in init.named_parameters()]
+        train_names = ["module." + n for n, p in init.named_parameters() if p.requires_grad]
+        shapes = {"module." + n: list(p.shape) for n, p in init.named_parameters()}
+        theta0 = flat(init.parameters())
+        common = dict(data_path=tmp, results_dir=os.path.join(tmp, "results"), model="DiT-tiny", image_size=64,
+                      num_classes=10, batch_size=2, seed=0, vae="ema", num_workers=0, log_every=10 ** 9, ckpt=ckpt,
+                      forget_class=3, mask_path=os.path.join(tmp, "mask"))
+        # python generate_fisher.py ...   (DiT/generate_fisher.py:131-293)
+        with Recorder() as rec:
+            gf_mod.main(argparse.Namespace(n_iters=n_fisher, **common))
+        assert len(rec.records) == 2 * n_fisher
+        fdir = os.path.join(tmp, "mask", "3")
+        ff, rf = torch.load(os.path.join(fdir, "forget_fisher.pt")), torch.load(os.path.join(fdir, "remain_fisher.pt"))
+        assert list(ff.keys()) == pnames and ff["module.pos_embed"] == 0
+        fixture = dict(names=pnames, train_names=train_names, shapes=shapes, theta0=theta0, n_fisher=n_fisher,
+                       fisher=dict(forget_grads=torch.stack(rec.records[:n_fisher]),
+                                   remain_grads=torch.stack(rec.records[n_fisher:]),
+                                   forget_fisher=flat([ff[n] for n in train_names]),
+                                   remain_fisher=flat([rf[n] for n in train_names])))
+        # python generate_mask.py ...   (DiT/generate_mask.py:16-46)
+        gm_mod.main(argparse.Namespace(mask_path=os.path.join(tmp, "mask"), forget_class=[3], thresholds=[1.0]))
+        mpath = os.path.join(fdir, "fisher_1.0.pt")
+        mask = torch.load(mpath)
+        assert mask["module.pos_embed"] == 0
+        fixture["ratio_mask"] = torch.cat([mask[n].reshape(-1) for n in train_names]).to(torch.uint8)
+        # python forget.py --method ron --unlearn-loss ga ...   (DiT/forget.py:151-358)
+        fargs = argparse.Namespace(n_iters=n_iters, lr=1e-4, ckpt_every=10 ** 9, snapshot_every=10 ** 9, method="ron",
+                                   unlearn_loss="ga", grad_clip=1.0, forget_alpha=0.05, decay_forget_alpha=False,
+                                   remain_alpha=1.0, **{**common, "mask_path": mpath})
+        with Recorder() as rec:
+            fg_mod.main(fargs)
+        assert len(rec.records) == 2 * n_iters
+        (ck,) = [os.path.join(dp, f) for dp, _, fs in os.walk(common["results_dir"]) for f in fs if f.endswith(".pt")]
+        ck = torch.load(ck, weights_only=False)
+        st = ck["opt"]["state"]
+        bare = [n[len("module."):] for n in pnames]
+        fixture["forget"] = dict(grads=torch.stack(rec.records), kinds=["forget", "remain"] * n_iters,
+                                 theta=flat([ck["model"][n] for n in pnames]), ema=flat([ck["ema"][n] for n in bare]),
+                                 opt_state_keys=sorted(st.keys()), opt_steps=[float(st[i]["step"]) for i in sorted(st)],
+                                 exp_avg=flat([st[i]["exp_avg"] for i in sorted(st)]),
+                                 exp_avg_sq=flat([st[i]["exp_avg_sq"] for i in sorted(st)]),
+                                 ckpt_keys=list(ck.keys()), model_keys=list(ck["model"].keys()), ema_keys=list(ck["ema"].keys()),
+                                 hyper=dict(lr=fargs.lr, grad_clip=fargs.grad_clip, decay=0.9999, n_iters=n_iters))
+    torch.save(fixture, os.path.join(OUT, "dit_scripts.pt"))
+    print("wrote dit scripts: N trainable =", fixture["fisher"]["forget_fisher"].numel(), "of", theta0.numel())
+
+
 PARTS = {
     "cls_default": lambda: classification("default", ema_beta=1.0),
     "cls_beta09": lambda: classification("beta09", ema_beta=0.9),
@@ -553,6 +752,7 @@ PARTS = {
     "ddpm_loop": ddpm_loop,
     "ddpm_runner": ddpm_runner,
     "dit_loop": dit_loop,
+    "dit_scripts": dit_scripts,
 }
 
 if __name__ == "__main__":

@@ -278,6 +278,67 @@ def test_ddpm_runner_dropin_against_whole_reference_methods(dev, tmp_path):
     check_final(un, rec, len(rec["grads"]))
 
 
+def test_dit_scripts_dropin_against_whole_reference_scripts(dev, tmp_path):
+    """The DiT family against DiT/generate_fisher.py, generate_mask.py and forget.py EXECUTED WHOLE (fixture
+    dit_scripts.pt): Fisher files, the mask CLI, the ron loop (eager and from one CUDA graph) and the checkpoint."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from dit_xl2 import DiTXL2Harness
+    from sfron_b200.methods.diffusion import DiffusionUnlearner
+    from sfron_b200.methods.masks import generate_mask_dit
+    fx = load_golden("dit_scripts.pt")
+    pnames, tnames = fx["names"], fx["train_names"]
+    names = [n[len("module."):] for n in pnames]
+    shapes = {k[len("module."):]: v for k, v in fx["shapes"].items()}
+
+    def fresh():
+        model = DiTXL2Harness(input_size=8, patch=8, width=8, depth=1, heads=2, classes=10)
+        assert [(n, list(p.shape)) for n, p in model.named_parameters()] == [(n, shapes[n]) for n in names]
+        set_flat(model, fx["theta0"], names, shapes)
+        return DiffusionUnlearner(model.to(dev), "dit", lr=fx["forget"]["hyper"]["lr"])
+
+    un, fi = fresh(), fx["fisher"]
+    fdir = tmp_path / "mask" / "3"
+    for which in ("forget", "remain"):
+        grads = fi[f"{which}_grads"]
+        un.generate_fisher(which, len(grads), lambda i: inject(un.model, grads[i]), out_dir=str(fdir))
+        d = torch.load(fdir / f"{which}_fisher.pt", weights_only=False)
+        assert list(d.keys()) == pnames and d["module.pos_embed"] == 0
+        got = torch.cat([d[n].reshape(-1) for n in tnames])
+        assert torch.equal(got.view(torch.int32), fi[f"{which}_fisher"].view(torch.int32)), which     # K1 is bit-exact
+    (path,) = generate_mask_dit(str(tmp_path / "mask"), [3], [1.0])
+    assert os.path.basename(path) == "fisher_1.0.pt"
+    mask = torch.load(path, weights_only=False)
+    assert mask["module.pos_embed"] == 0 and mask[tnames[0]].dtype == torch.bool
+    assert torch.equal(torch.cat([mask[n].reshape(-1) for n in tnames]).to(torch.uint8), fx["ratio_mask"])
+
+    rec = fx["forget"]
+    gf, gr = rec["grads"][0::2], rec["grads"][1::2]
+    for graphed in (False, True):
+        un = fresh()
+        un.load_mask(path)
+        if graphed:
+            gf_s, gr_s = torch.zeros_like(gf[0], device=dev), torch.zeros_like(gr[0], device=dev)
+
+            def refill(i):
+                gf_s.copy_(gf[i])
+                gr_s.copy_(gr[i])
+            un.forget(len(gf), lambda i: inject(un.model, gf_s), lambda i: inject(un.model, gr_s), cuda_graph=True, refill=refill)
+        else:
+            un.forget(len(gf), lambda i: inject(un.model, gf[i]), lambda i: inject(un.model, gr[i]))
+        final = torch.cat([p.detach().reshape(-1) for p in un.model.parameters()])          # frozen pos_embed included
+        assert close(final, rec["theta"]), graphed
+        ck = un.checkpoint(step=len(gf), args=argparse.Namespace(lr=1e-4))
+        assert list(ck.keys()) == rec["ckpt_keys"]
+        assert list(ck["model"].keys()) == rec["model_keys"] and list(ck["ema"].keys()) == rec["ema_keys"]
+        assert close(torch.cat([ck["ema"][n].reshape(-1) for n in names]), rec["ema"]), graphed
+        st = ck["opt"]["state"]
+        assert sorted(st.keys()) == rec["opt_state_keys"]                                    # no slot for frozen pos_embed
+        assert [float(st[i]["step"]) for i in sorted(st)] == rec["opt_steps"]
+        assert close(torch.cat([st[i]["exp_avg"].reshape(-1) for i in sorted(st)]), rec["exp_avg"])
+        assert close(torch.cat([st[i]["exp_avg_sq"].reshape(-1) for i in sorted(st)]), rec["exp_avg_sq"])
+
+
 def test_bf16_model_mixed_precision_flat_params(dev):
     """BASELINE config 3 (bf16): module weights / grads are bf16 views, the kernels keep an fp32 master."""
     import sfron_b200 as sfr

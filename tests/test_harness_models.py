@@ -112,3 +112,18 @@ def test_sd_unet_matches_reference_module():
     with torch.no_grad():
         a, b = ref(z, t, context=ctx), ours(z, t, ctx)
     assert torch.allclose(a, b, rtol=1e-4, atol=1e-4), (a - b).abs().max()
+
+
+def test_dit_harness_structure_matches_reference_class():
+    """tools/dit_xl2.py at the size of the recorded reference run (tests/golden/dit_scripts.pt was produced by the
+    reference's own `DiT` class): same names, shapes and order, frozen `pos_embed` first; full-size counts."""
+    from conftest import load_golden
+    from dit_xl2 import DiTXL2Harness
+    fx = load_golden("dit_scripts.pt")
+    tiny = DiTXL2Harness(input_size=8, patch=8, width=8, depth=1, heads=2, classes=10)
+    assert [("module." + n, list(p.shape)) for n, p in tiny.named_parameters()] == [(n, fx["shapes"][n]) for n in fx["names"]]
+    assert ["module." + n for n, p in tiny.named_parameters() if p.requires_grad] == fx["train_names"]
+    with torch.device("meta"):
+        full = DiTXL2Harness()
+    assert sum(p.numel() for p in full.parameters()) == 675_129_632 and len(list(full.parameters())) == 292
+    assert sum(p.numel() for p in full.parameters() if p.requires_grad) == 674_834_720

@@ -192,3 +192,41 @@ def test_ddpm_runner_saliency_unlearn():
         loop.forget_step(unflat(g, names, shapes), mask=mask, max_norm=hp["grad_clip"], order="clip_then_mask")
         loop.slow_update()
     _check_runner_final(loop, rec)
+
+
+def test_dit_scripts_executed_whole():
+    """DiT/generate_fisher.py, generate_mask.py and forget.py run as scripts (fixture dit_scripts.pt): Fisher bit-exact,
+    mask bit-exact (frozen pos_embed keeps the int-0 placeholder), AdamW + clip + EMA trajectory within 1e-6."""
+    fx = load_golden("dit_scripts.pt")
+    names, tnames, shapes = fx["names"], fx["train_names"], fx["shapes"]
+    tshapes = {n: shapes[n] for n in tnames}
+    fi = fx["fisher"]
+    acc = {}
+    for which in ("forget", "remain"):
+        acc[which] = O.fisher_init(names)
+        for g in fi[f"{which}_grads"]:
+            O.fisher_accumulate(acc[which], {**{n: None for n in names}, **unflat(g, tnames, tshapes)}, fx["n_fisher"])
+        assert acc[which]["module.pos_embed"] == 0                    # never received a gradient
+        got = torch.cat([acc[which][n].reshape(-1) for n in tnames])
+        assert bits_equal(got, fi[f"{which}_fisher"]), which
+    masks, _, _ = O.ratio_mask(acc["forget"], acc["remain"], 1.0)
+    assert masks["module.pos_embed"] == 0
+    assert torch.equal(torch.cat([masks[n].reshape(-1) for n in tnames]).to(torch.uint8), fx["ratio_mask"])
+    rec, hp = fx["forget"], fx["forget"]["hyper"]
+    theta0 = unflat(fx["theta0"], names, shapes)
+    loop = O.FlatReferenceLoop(tshapes, theta0, "adamw", dict(lr=hp["lr"], weight_decay=0.0), ema_mode="dit", ema_a=hp["decay"])
+    frozen = {n: theta0[n] for n in names if n not in tnames}
+    frozen_ema = {n: t.clone() for n, t in frozen.items()}
+    mask = {n: masks[n] for n in tnames}
+    for kind, g in zip(rec["kinds"], rec["grads"]):
+        gd = unflat(g, tnames, tshapes)
+        if kind == "forget":
+            loop.forget_step(gd, mask=mask, max_norm=hp["grad_clip"])
+        else:
+            loop.remain_step(gd, max_norm=None, ema=True)
+            O.ema_dit_(frozen_ema, frozen, hp["decay"])
+    got_p = torch.cat([(loop.params[n].detach() if n in tnames else frozen[n]).reshape(-1) for n in names])
+    got_e = torch.cat([(loop.slow[n] if n in tnames else frozen_ema[n]).reshape(-1) for n in names])
+    assert _close(got_p, rec["theta"]) and _close(got_e, rec["ema"])
+    assert _close(loop.flat("m"), rec["exp_avg"]) and _close(loop.flat("v"), rec["exp_avg_sq"])
+    assert rec["opt_state_keys"] == list(range(1, len(names))) and set(rec["opt_steps"]) == {2.0 * hp["n_iters"]}
