@@ -21,6 +21,11 @@ What is executed from the reference, unmodified:
     config 3 executed whole on a 1-block DiT built by the reference's own `DiT` class, with: stubs for the two
     absent third-party imports (timm's PatchEmbed/Attention/Mlp, diffusers' AutoencoderKL), the one
     `assert torch.cuda.is_available()` statement removed, synthetic datasets for get_unlearn_dataset
+  * SD/train-scripts/generate_fisher.py generate_nsfw_fisher(), generate_fisher_mask.py (subprocess),
+    nsfw_removal.py nsfw_removal(), gradient_ascent.py gradient_ascent() — whole functions of config 4, with
+    `dataset.setup_model` returning a stand-in for LatentDiffusion (its five members the scripts use, around a
+    586-parameter U-Net), synthetic image loaders, and stub modules for matplotlib / convertModels / diffusers /
+    ldm's DDIMSampler (none of which touch the path)
 The forget-loop bodies of DDPM/runners/diffusion.py:1122-1180 and DiT/forget.py:285-322 are
 inline in 1000-line methods that need datasets and full-size models; for those the script
 drives the reference's OWN optimizer / EMA objects with synthetic gradients in the order of
@@ -740,6 +745,207 @@ def dit_scripts():
     print("wrote dit scripts: N trainable =", fixture["fisher"]["forget_fisher"].numel(), "of", theta0.numel())
 
 
+# ------------------------------------------------------- SD train-scripts, executed whole (config 4)
+class TinyLatentUNet(nn.Module):
+    """Stand-in for the 860 M-parameter LDM U-Net behind `model.model.diffusion_model` (the real one needs
+    pytorch_lightning / omegaconf / CLIP weights, and one recorded gradient of even its narrowest legal
+    instance is ~1 MB): `forward(x, t, context)` with a cross-attention named `attn2`, 586 parameters."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv_in = nn.Conv2d(4, 6, 3, padding=1)
+        self.temb = nn.Linear(1, 6)
+        self.attn2 = nn.Module()
+        self.attn2.to_q = nn.Linear(6, 6, bias=False)
+        self.attn2.to_k = nn.Linear(8, 6, bias=False)
+        self.attn2.to_v = nn.Linear(8, 6, bias=False)
+        self.conv_out = nn.Conv2d(6, 4, 3, padding=1)
+
+    def forward(self, x, t, context):
+        h = self.conv_in(x) + self.temb(t[:, None].float() / 1000.0)[:, :, None, None]
+        b, c, hh, ww = h.shape
+        q = self.attn2.to_q(h.flatten(2).transpose(1, 2))
+        att = torch.softmax(q @ self.attn2.to_k(context).transpose(1, 2) / c ** 0.5, dim=-1)
+        h = h + (att @ self.attn2.to_v(context)).transpose(1, 2).reshape(b, c, hh, ww)
+        return self.conv_out(torch.tanh(h))
+
+
+class FakeLatentDiffusion(nn.Module):
+    """The five LatentDiffusion members the train-scripts touch (SD/ldm/models/diffusion/ddpm.py): get_input,
+    q_sample, apply_model, shared_step, num_timesteps — around TinyLatentUNet, with a fixed "VAE" (8x average
+    pooling) and a fixed "text encoder" (embedding seeded by the prompt string)."""
+    first_stage_key = "jpg"
+    num_timesteps = 1000
+    instances = []
+
+    def __init__(self):
+        super().__init__()
+        self.model = nn.Module()
+        self.model.diffusion_model = TinyLatentUNet()
+        betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float64) ** 2
+        self.register_buffer("alphas_cumprod", torch.cumprod(1 - betas, 0).float())
+        self.cond_stage_model = argparse.Namespace(device="cpu")
+        FakeLatentDiffusion.instances.append(self)
+
+    @property
+    def device(self):
+        return torch.device("cpu")
+
+    def get_input(self, batch, k):
+        x = batch[k].permute(0, 3, 1, 2)
+        z = torch.nn.functional.avg_pool2d(x, 8)
+        z = torch.cat([z, z.mean(1, keepdim=True)], dim=1)
+        embs = []
+        for prompt in batch["txt"]:
+            g = torch.Generator().manual_seed(sum(prompt.encode()) + 1)
+            embs.append(torch.randn(5, 8, generator=g))
+        return z, torch.stack(embs)
+
+    def q_sample(self, x_start, t, noise):
+        a = self.alphas_cumprod[t].view(-1, 1, 1, 1)
+        return a.sqrt() * x_start + (1 - a).sqrt() * noise
+
+    def apply_model(self, x_noisy, t, cond):
+        return self.model.diffusion_model(x_noisy, t, cond)
+
+    def shared_step(self, batch):
+        x, c = self.get_input(batch, self.first_stage_key)
+        t = torch.randint(0, self.num_timesteps, (x.shape[0],)).long()
+        noise = torch.randn_like(x)
+        loss = torch.nn.functional.mse_loss(self.apply_model(self.q_sample(x, t, noise), t, c), noise)
+        return loss, {}
+
+
+def sd_scripts():
+    from torch.utils.data import DataLoader, Dataset, TensorDataset
+    scripts = os.path.join(REF, "SD/train-scripts")
+    sys.path.insert(0, scripts)
+
+    def module(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    # imports of the scripts that are absent here or need weights / datasets
+    noop = lambda *a, **k: None
+    module("matplotlib", pyplot=module("matplotlib.pyplot", plot=noop, legend=noop, title=noop, xlabel=noop,
+                                       ylabel=noop, savefig=noop))
+    module("convertModels", savemodelDiffusers=noop)
+    module("diffusers", LMSDiscreteScheduler=lambda **k: None)
+    module("ldm"); module("ldm.models"); module("ldm.models.diffusion")
+    module("ldm.models.diffusion.ddim", DDIMSampler=lambda model: None)
+
+    class Images(Dataset):
+        def __init__(self, x):
+            self.x = x
+
+        def __len__(self):
+            return len(self.x)
+
+        def __getitem__(self, i):
+            return self.x[i]
+
+    g = torch.Generator().manual_seed(51)
+    nude, clothed = torch.rand(4, 3, 32, 32, generator=g) * 2 - 1, torch.rand(6, 3, 32, 32, generator=g) * 2 - 1
+    labels = torch.randint(1, 4, (6,), generator=g)
+    bs = 2
+
+    def setup_model(config, ckpt, device):
+        torch.manual_seed(50)                         # every script starts from the same weights
+        return FakeLatentDiffusion()
+
+    module("dataset", setup_model=setup_model,
+           setup_forget_nsfw_data=lambda batch_size, image_size: (DataLoader(Images(nude), batch_size=batch_size),
+                                                                  DataLoader(Images(clothed), batch_size=batch_size)),
+           setup_forget_data=lambda c, batch_size, image_size: (DataLoader(TensorDataset(nude, torch.zeros(4, dtype=torch.long)),
+                                                                             batch_size=batch_size), None),
+           setup_remain_data=lambda c, batch_size, image_size: (DataLoader(TensorDataset(clothed, labels), batch_size=batch_size),
+                                                                 [f"an image of a thing {i}" for i in range(4)]))
+    gf = importlib.import_module("generate_fisher")
+    nr = importlib.import_module("nsfw_removal")
+    ga = importlib.import_module("gradient_ascent")
+
+    class Recorder:
+        def __init__(self):
+            self.records, self._orig = [], torch.Tensor.backward
+
+        def __enter__(self):
+            rec = self
+
+            def backward(t, *a, **k):
+                out = rec._orig(t, *a, **k)
+                unet = FakeLatentDiffusion.instances[-1].model.diffusion_model
+                rec.records.append(flat([p.grad if p.grad is not None else torch.zeros_like(p) for p in unet.parameters()]))
+                return out
+            torch.Tensor.backward = backward
+            return self
+
+        def __exit__(self, *exc):
+            torch.Tensor.backward = self._orig
+
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)                                 # the scripts write to cwd-relative fisher/ and models/
+        try:
+            os.makedirs("fisher")
+            ref_model = setup_model(None, None, "cpu")
+            unet = ref_model.model.diffusion_model
+            names = [n for n, _ in unet.named_parameters()]
+            shapes = {n: list(p.shape) for n, p in unet.named_parameters()}
+            fixture = dict(names=names, shapes=shapes, theta0=flat(unet.parameters()),
+                           full_names=[n for n, _ in ref_model.named_parameters()])
+            # generate_fisher.py: generate_nsfw_fisher (SD/train-scripts/generate_fisher.py:8-129)
+            torch.manual_seed(52)
+            with Recorder() as rec:
+                gf.generate_nsfw_fisher(7.5, bs, 1, 1e-5, None, None, None, "cpu", image_size=32)
+            nf, nrm = len(nude) // bs, len(clothed) // bs
+            assert len(rec.records) == nf + nrm
+            ff, rf = torch.load("fisher/nude_forget.pt"), torch.load("fisher/nude_remain.pt")
+            assert list(ff.keys()) == names
+            fixture["fisher"] = dict(forget_grads=torch.stack(rec.records[:nf]), remain_grads=torch.stack(rec.records[nf:]),
+                                     forget_fisher=flat([ff[n] for n in names]), remain_fisher=flat([rf[n] for n in names]))
+            # generate_fisher_mask.py, unmodified, as a subprocess (:27-48)
+            subprocess.run([sys.executable, os.path.join(scripts, "generate_fisher_mask.py"), "--ckpt_folder", "fisher",
+                            "--threshold", "1.0"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            mask = torch.load("fisher/nude_mask_1.0.pt")
+            fixture["ratio_mask"] = torch.cat([mask[n].reshape(-1) for n in names]).to(torch.uint8)
+
+            def final_weights():
+                (path,) = [os.path.join(dp, f) for dp, _, fs in os.walk("models") for f in fs if f.endswith(".pt")]
+                sd = torch.load(path)
+                out = flat([sd["model.diffusion_model." + n] for n in names])
+                import shutil
+                shutil.rmtree("models")
+                return out
+
+            # nsfw_removal.py (:38-214): forget step + remain step per iteration, Adam, no clip, no EMA.  Its mask
+            # multiply is guarded by `n in parameters` (a str looked up in a list of tensors, :157-160): never true.
+            n_iters = 3
+            torch.manual_seed(53)
+            with Recorder() as rec:
+                nr.nsfw_removal("full", 1.0, 0.5, bs, n_iters, 1e-4, None, None, "fisher", None, "cpu",
+                                mask_threshold=1.0, image_size=32)
+            assert len(rec.records) == 2 * n_iters
+            fixture["nsfw_removal"] = dict(grads=torch.stack(rec.records), theta=final_weights(), lr=1e-4, mask_applied=False)
+            # gradient_ascent.py (:14-122), the sibling whose mask multiply does fire: ONE backward of the joint loss
+            # per iteration, grad *= mask, Adam.  (Its last line, save_history(losses, name, classes), names an
+            # undefined variable; the weights are on disk by then.)
+            torch.manual_seed(54)
+            with Recorder() as rec:
+                try:
+                    ga.gradient_ascent(0, "full", 0.7, bs, 2, 1e-4, None, None, "fisher/nude_mask_1.0.pt", None, "cpu",
+                                       image_size=32)
+                except NameError as e:
+                    assert "classes" in str(e)
+            assert len(rec.records) == 2 * (len(nude) // bs)
+            fixture["gradient_ascent"] = dict(grads=torch.stack(rec.records), theta=final_weights(), lr=1e-4, mask_applied=True)
+        finally:
+            os.chdir(cwd)
+    torch.save(fixture, os.path.join(OUT, "sd_scripts.pt"))
+    print("wrote sd scripts: N =", fixture["theta0"].numel())
+
+
 PARTS = {
     "cls_default": lambda: classification("default", ema_beta=1.0),
     "cls_beta09": lambda: classification("beta09", ema_beta=0.9),
@@ -753,6 +959,7 @@ PARTS = {
     "ddpm_runner": ddpm_runner,
     "dit_loop": dit_loop,
     "dit_scripts": dit_scripts,
+    "sd_scripts": sd_scripts,
 }
 
 if __name__ == "__main__":

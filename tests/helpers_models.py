@@ -38,6 +38,21 @@ class TinyCond(nn.Module):
         self.conv_out = nn.Conv2d(6, 3, 3, padding=1)
 
 
+class TinyLatentUNet(nn.Module):
+    """Parameter structure of the 586-parameter stand-in U-Net make_golden.py's `sd_scripts` part put behind
+    `model.model.diffusion_model` (keys are U-Net-local, as in the SD Fisher / mask files)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv_in = nn.Conv2d(4, 6, 3, padding=1)
+        self.temb = nn.Linear(1, 6)
+        self.attn2 = nn.Module()
+        self.attn2.to_q = nn.Linear(6, 6, bias=False)
+        self.attn2.to_k = nn.Linear(8, 6, bias=False)
+        self.attn2.to_v = nn.Linear(8, 6, bias=False)
+        self.conv_out = nn.Conv2d(6, 4, 3, padding=1)
+
+
 def loaders(seed):
     g = torch.Generator().manual_seed(seed)
     fx, fy = torch.randn(12, 3, 8, 8, generator=g), torch.randint(0, 10, (12,), generator=g)

@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from conftest import load_golden, unflat
-from helpers_models import TinyCond, TinyDiT, TinyNet, inject, loaders
+from helpers_models import TinyCond, TinyDiT, TinyLatentUNet, TinyNet, inject, loaders
 
 pytestmark = pytest.mark.gpu
 
@@ -337,6 +337,51 @@ def test_dit_scripts_dropin_against_whole_reference_scripts(dev, tmp_path):
         assert [float(st[i]["step"]) for i in sorted(st)] == rec["opt_steps"]
         assert close(torch.cat([st[i]["exp_avg"].reshape(-1) for i in sorted(st)]), rec["exp_avg"])
         assert close(torch.cat([st[i]["exp_avg_sq"].reshape(-1) for i in sorted(st)]), rec["exp_avg_sq"])
+
+
+def test_sd_scripts_dropin_against_whole_reference_scripts(dev, tmp_path):
+    """The SD family against generate_fisher.py / generate_fisher_mask.py / nsfw_removal.py / gradient_ascent.py
+    EXECUTED WHOLE (fixture sd_scripts.pt): U-Net-local keys, Adam, no clip, no EMA."""
+    from sfron_b200.methods.diffusion import DiffusionUnlearner
+    from sfron_b200.methods.masks import generate_fisher_mask
+    fx = load_golden("sd_scripts.pt")
+    names, shapes, fi = fx["names"], fx["shapes"], fx["fisher"]
+
+    def fresh(lr):
+        model = TinyLatentUNet()
+        assert [n for n, _ in model.named_parameters()] == names
+        set_flat(model, fx["theta0"], names, shapes)
+        return DiffusionUnlearner(model.to(dev), "sd", lr=lr)
+
+    un = fresh(1e-5)
+    fdir = tmp_path / "fisher"
+    for which, fname in (("forget", "nude_forget.pt"), ("remain", "nude_remain.pt")):
+        grads = fi[f"{which}_grads"]
+        un.generate_fisher(which, len(grads), lambda i: inject(un.model, grads[i]), out_dir=str(fdir))
+        d = torch.load(fdir / fname, weights_only=False)
+        assert list(d.keys()) == names                                         # no "module." / "model.diffusion_model." prefix
+        got = torch.cat([d[n].reshape(-1) for n in names])
+        assert torch.equal(got.view(torch.int32), fi[f"{which}_fisher"].view(torch.int32)), which
+    path = generate_fisher_mask(str(fdir), 1.0, forget_name="nude_forget.pt", remain_name="nude_remain.pt",
+                                out_fmt="nude_mask_{th}.pt")
+    assert os.path.basename(path) == "nude_mask_1.0.pt"
+    mask = torch.load(path, weights_only=False)
+    assert torch.equal(torch.cat([mask[n].reshape(-1) for n in names]).to(torch.uint8), fx["ratio_mask"])
+    # nsfw_removal.py as it actually behaves: its `n in parameters` guard never fires, so no mask is applied
+    rec = fx["nsfw_removal"]
+    un = fresh(rec["lr"])
+    un.load_mask(path)
+    gf, gr = rec["grads"][0::2], rec["grads"][1::2]
+    un.forget(len(gf), lambda i: inject(un.model, gf[i]), lambda i: inject(un.model, gr[i]), use_mask=rec["mask_applied"])
+    assert close(torch.cat([p.detach().reshape(-1) for p in un.model.parameters()]), rec["theta"])
+    # gradient_ascent.py: one masked Adam step per iteration on the joint loss (saliency_unlearn without clip / EMA)
+    rec = fx["gradient_ascent"]
+    un = fresh(rec["lr"])
+    un.load_mask(path)
+    un.saliency_unlearn(len(rec["grads"]), lambda i: inject(un.model, rec["grads"][i]), use_mask=rec["mask_applied"])
+    assert close(torch.cat([p.detach().reshape(-1) for p in un.model.parameters()]), rec["theta"])
+    sd = un.checkpoint()
+    assert list(sd.keys()) == names                                            # plain state_dict, as save_model writes
 
 
 def test_bf16_model_mixed_precision_flat_params(dev):

@@ -230,3 +230,40 @@ def test_dit_scripts_executed_whole():
     assert _close(got_p, rec["theta"]) and _close(got_e, rec["ema"])
     assert _close(loop.flat("m"), rec["exp_avg"]) and _close(loop.flat("v"), rec["exp_avg_sq"])
     assert rec["opt_state_keys"] == list(range(1, len(names))) and set(rec["opt_steps"]) == {2.0 * hp["n_iters"]}
+
+
+def test_sd_scripts_executed_whole():
+    """SD/train-scripts generate_fisher.py, generate_fisher_mask.py, nsfw_removal.py and gradient_ascent.py run whole
+    (fixture sd_scripts.pt).  nsfw_removal.py never applies its mask (`n in parameters`, :157-160); the sibling
+    gradient_ascent.py does (:94-99) — both behaviours are pinned."""
+    fx = load_golden("sd_scripts.pt")
+    names, shapes, fi = fx["names"], fx["shapes"], fx["fisher"]
+    assert fx["full_names"] == ["model.diffusion_model." + n for n in names]       # what `n.split(...)[-1]` strips
+    acc = {}
+    for which in ("forget", "remain"):
+        grads = fi[f"{which}_grads"]
+        acc[which] = O.fisher_init(names)
+        for g in grads:
+            O.fisher_accumulate(acc[which], unflat(g, names, shapes), len(grads))
+        assert bits_equal(torch.cat([acc[which][n].reshape(-1) for n in names]), fi[f"{which}_fisher"]), which
+    masks, _, _ = O.ratio_mask(acc["forget"], acc["remain"], 1.0)
+    assert torch.equal(torch.cat([masks[n].reshape(-1) for n in names]).to(torch.uint8), fx["ratio_mask"])
+    theta0 = unflat(fx["theta0"], names, shapes)
+    # nsfw_removal: forget step then remain step, one Adam, no mask in effect, no clip, no EMA
+    rec = fx["nsfw_removal"]
+    loop = O.FlatReferenceLoop(shapes, theta0, "adam", dict(lr=rec["lr"]))
+    for i, g in enumerate(rec["grads"]):
+        gd = unflat(g, names, shapes)
+        loop.forget_step(gd, mask=None) if i % 2 == 0 else loop.remain_step(gd, ema=False)
+    assert _close(loop.flat("p"), rec["theta"])
+    masked = O.FlatReferenceLoop(shapes, theta0, "adam", dict(lr=rec["lr"]))
+    for i, g in enumerate(rec["grads"]):
+        gd = unflat(g, names, shapes)
+        masked.forget_step(gd, mask=masks) if i % 2 == 0 else masked.remain_step(gd, ema=False)
+    assert not _close(masked.flat("p"), rec["theta"])                              # the mask really is not applied there
+    # gradient_ascent: one masked step per iteration on the joint loss
+    rec = fx["gradient_ascent"]
+    loop = O.FlatReferenceLoop(shapes, theta0, "adam", dict(lr=rec["lr"]))
+    for g in rec["grads"]:
+        loop.forget_step(unflat(g, names, shapes), mask=masks)
+    assert _close(loop.flat("p"), rec["theta"])
