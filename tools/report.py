@@ -4,6 +4,10 @@ import json, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = os.path.join(ROOT, "profiles")
 rows = [json.loads(l) for l in open(os.path.join(P, "r1_sweep.jsonl"))]
+# the K2b rows were re-measured after the select became two-pass: those lines supersede the first sweep's
+two_pass = [json.loads(l) for l in open(os.path.join(P, "r1_sweep_select_two_pass.jsonl"))]
+fresh = {(r["n"], r["kernel"]) for r in two_pass}
+rows = two_pass + [r for r in rows if (r["n"], r["kernel"]) not in fresh]
 def get(n, k, dt=None):
     for r in rows:
         if r["n"] == n and r["kernel"] == k and (dt is None or r["grad_dtype"] == dt):
@@ -21,11 +25,12 @@ spec = [("K1 `fisher_accum`", "fisher_accum", "f32", "bit-exact"), ("K1, 4 per-s
         ("K3 AdamW + EMA, bf16 gradients", "fused_update_adamw_ema", "bf16", "1e-6 on the fp32 master"),
         ("K3 SGD-momentum masked", "fused_update_sgd_masked", "f32", "1e-6"), ("K3 SGD-momentum + slow-fast", "fused_update_sgd_slowfast", "f32", "1e-6"),
         ("K2b top-k select, total", "topk_select_total", None, "mask bit-exact (stable ties)"),
-        ("K2b hist pass 0 / pass 1 / apply", None, None, "")]
+        ("K2b top-k select, three-read fallback form", "topk_select_total_three_reads", None, "mask bit-exact (identical bytes)"),
+        ("K2b hist pass 0 / pass 1 + provisional mask / candidate-only apply", None, None, "")]
 for name, k, dt, par in spec:
     if k is None:
-        a, b, c = get(N3, "topk_hist_pass0"), get(N3, "topk_hist_pass1"), get(N3, "topk_apply")
-        print(f"| 3 | 1 | {name} | 4 / 4 / 5 | {cell(a)} / {cell(b)} / {cell(c)} | {frac(a)} / {frac(b)} / {frac(c)} | |")
+        a, b, c = get(N3, "topk_hist_pass0"), get(N3, "topk_hist_pass1_with_mask"), get(N3, "topk_apply_candidates_only")
+        print(f"| 3 | 1 | {name} | 4 / 5 / — | {cell(a)} / {cell(b)} / {c['ms']} ms | {frac(a)} / {frac(b)} / — | |")
         continue
     r = get(N3, k, dt)
     print(f"| 3 (N3 = 675,129,632) | 1 | {name} | {r['bytes_per_elem']} | {cell(r)} | {frac(r)} | {par} |")
@@ -45,3 +50,7 @@ for f in ("r1_dit_e2e_1gpu.jsonl", "r1_dit_e2e_2gpu.jsonl", "r1_dit_e2e_8gpu.jso
     for l in open(os.path.join(P, f)):
         r = json.loads(l)
         print(f, r["n_gpus"], {k: {a: round(b, 2) for a, b in v.items()} for k, v in r.items() if isinstance(v, dict)})
+print()
+for l in open(os.path.join(P, "r1_unet_e2e_1gpu.jsonl")):
+    r = json.loads(l)
+    print("unet_e2e", r["family"], r["params"], {k: v for k, v in r.items() if k in ("stock", "ours", "speedup", "mask_agreement")})
