@@ -306,6 +306,12 @@ def test_dit_scripts_dropin_against_whole_reference_scripts(dev, tmp_path):
         assert list(d.keys()) == pnames and d["module.pos_embed"] == 0
         got = torch.cat([d[n].reshape(-1) for n in tnames])
         assert torch.equal(got.view(torch.int32), fi[f"{which}_fisher"].view(torch.int32)), which     # K1 is bit-exact
+    # the same Fisher loop with forward + backward + K1 replayed from one CUDA graph: still bit-exact
+    ung = fresh()
+    g_s = torch.zeros_like(fi["forget_grads"][0], device=dev)
+    ung.generate_fisher("forget", len(fi["forget_grads"]), lambda i: inject(ung.model, g_s), cuda_graph=True,
+                        refill=lambda i: g_s.copy_(fi["forget_grads"][i]))
+    assert torch.equal(ung.mhp.hp.forget_fisher.cpu().view(torch.int32), fi["forget_fisher"].view(torch.int32))
     (path,) = generate_mask_dit(str(tmp_path / "mask"), [3], [1.0])
     assert os.path.basename(path) == "fisher_1.0.pt"
     mask = torch.load(path, weights_only=False)

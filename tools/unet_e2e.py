@@ -93,13 +93,14 @@ class Family:
         """One synthetic batch (fresh tensors) for the forget / remain losses."""
         return self._ddpm_batch(forget) if self.name == "ddpm" else self._sd_batch()
 
-    def fisher_loss(self, forget):
+    def fisher_loss(self, forget, batch=None):
+        batch = self.draw(forget) if batch is None else batch
         if self.name == "ddpm":
             from ddpm_unet import eps_loss
-            x, t, c, e = self._ddpm_batch(forget)
+            x, t, c, e = batch
             return eps_loss(self.model, x, t, c, e, self.ac, mode="test", cond_scale=2.0)
         from sd_unet import guided_eps_loss
-        z, t, e = self._sd_batch()
+        z, t, e = batch
         ctx = (self.ctx_forget if forget else self.ctx_pseudo).expand(self.bs, -1, -1)
         return guided_eps_loss(self.model, z, t, ctx, self.ctx_null.expand(self.bs, -1, -1), e, self.ac, cond_scale=7.5)
 
@@ -223,10 +224,19 @@ def ours(fam: Family, n_fisher, n_iters, tmp, cuda_graph=False):
 
     def fisher_stage():
         fam.model.eval()
-        fam.reseed(1)
-        un.generate_fisher("forget", n_fisher, lambda i: fam.fisher_loss(True), out_dir=tmp)
-        fam.reseed(2)
-        un.generate_fisher("remain", n_fisher, lambda i: fam.fisher_loss(False), out_dir=tmp)
+        for which, forget, stream in (("forget", True, 1), ("remain", False, 2)):
+            fam.reseed(stream)
+            if not cuda_graph:
+                un.generate_fisher(which, n_fisher, lambda i: fam.fisher_loss(forget), out_dir=tmp)
+                continue
+            sb = fam.draw(forget)
+
+            def refill(i):
+                for dst, src in zip(sb, fam.draw(forget)):
+                    dst.copy_(src)
+
+            un.generate_fisher(which, n_fisher, lambda i: fam.fisher_loss(forget, sb), out_dir=tmp, cuda_graph=True,
+                               refill=refill)
 
     def mask_stage():
         return generate_fisher_mask(tmp, 1.0, forget_name=fam.fisher_names[0], remain_name=fam.fisher_names[1],

@@ -104,16 +104,49 @@ class DiffusionUnlearner:
                                 key_prefix=self.cfg.key_prefix, device=device)
 
     # ---- Fisher ------------------------------------------------------------------------------------
-    def generate_fisher(self, which: str, n_batches: int, loss_fn: LossFn, out_dir: Optional[str] = None) -> None:
+    def generate_fisher(self, which: str, n_batches: int, loss_fn: LossFn, out_dir: Optional[str] = None, *,
+                        cuda_graph: bool = False, refill: Optional[Callable[[int], None]] = None) -> None:
         """`F += grad**2 / n_batches` over `n_batches` backward passes of `loss_fn(i)`; written in the
-        reference's dict format to {out_dir}/{forget,remain}_fisher.pt (nude_*.pt for SD)."""
+        reference's dict format to {out_dir}/{forget,remain}_fisher.pt (nude_*.pt for SD).
+
+        cuda_graph=True: forward + backward + Fisher kernel of ONE batch captured once and replayed n_batches
+        times (the reference runs this loop for 2000 batches of one sample, DiT/generate_fisher.py:220-239);
+        `loss_fn` must then read its batch from static device tensors that `refill(i)` overwrites."""
         mhp = self.mhp
-        mhp.hp.buffer(f"{which}_fisher").zero_()
-        for i in range(n_batches):
+        acc = mhp.hp.buffer(f"{which}_fisher")
+        acc.zero_()
+        if cuda_graph:
+            if not mhp.flat.grads_as_views:
+                raise RuntimeError("cuda_graph=True needs view-gradients (FlatParams(grads_as_views=True))")
+            dev = mhp.flat.device
+
+            def body():
+                loss_fn(0).backward()
+                mhp.fisher_accumulate(which, float(n_batches), clip_max_norm=self.cfg.clip_fisher)
+                mhp.zero_grad()
+
+            if refill is not None:
+                refill(0)
             mhp.zero_grad()
-            loss_fn(i).backward()
-            mhp.fisher_accumulate(which, float(n_batches), clip_max_norm=self.cfg.clip_fisher)
-        mhp.zero_grad()
+            side = torch.cuda.Stream(device=dev)          # one eager pass outside the capture, then undone
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            acc.zero_()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+            for i in range(n_batches):
+                if refill is not None:
+                    refill(i)
+                graph.replay()
+        else:
+            for i in range(n_batches):
+                mhp.zero_grad()
+                loss_fn(i).backward()
+                mhp.fisher_accumulate(which, float(n_batches), clip_max_norm=self.cfg.clip_fisher)
+            mhp.zero_grad()
         if out_dir is not None:
             os.makedirs(out_dir, exist_ok=True)
             name = self.cfg.forget_fisher_name if which == "forget" else self.cfg.remain_fisher_name
