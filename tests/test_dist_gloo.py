@@ -96,6 +96,17 @@ def _select_protocol(rank, tmp):
         local_mask = (key > thr) | (tie & (rank_in_ties < budget))
         want = sg.local(O.topk_mask_flat(x, k)).bool()
         assert torch.equal(local_mask, want), (rank, k)
+        # the two-pass form the kernels use: pass 1 already wrote `prefix(key) > prefix` for every element and staged
+        # the prefix-matching ones; after scan 1 only that list is walked (low bits above the threshold's -> 1, ties
+        # ranked from the per-rank base), the vector is not read a third time
+        provisional = (key >> 16) > prefix
+        cand = torch.nonzero(sel).flatten()                       # staged (flat index, low 16 bits)
+        low = key[cand] & 0xFFFF
+        two_pass = provisional.clone()
+        two_pass[cand[low > b]] = True
+        ties = cand[low == b]
+        two_pass[ties[(base + torch.arange(ties.numel())) < budget]] = True
+        assert torch.equal(two_pass, want), (rank, k)
 
 
 def test_shards_and_collectives(tmp_path):
