@@ -5,7 +5,6 @@ standing in for the CUDA histogram kernels (which need a GPU)."""
 import os
 import sys
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

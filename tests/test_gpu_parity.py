@@ -4,7 +4,6 @@ fixtures.  Bar (BASELINE.json north_star): masks bit-exact; Fisher values and up
 within 1e-6 relative (fp32).  K1 / K2a / K2b are in fact bit-exact; K3 cannot be bit-exact
 against CPU torch because torch's AVX-512 `sqrt` is not correctly rounded.
 """
-import math
 
 import pytest
 import torch

@@ -6,7 +6,6 @@ Same parameter count and tensor count as the reference's Classification/models/r
 classifier.  Written for the end-to-end measurement of BASELINE config 1; the forward/backward of
 the reference's models stays in PyTorch and is outside the hot path's scope.
 """
-import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
