@@ -1,0 +1,236 @@
+// tune_hist1.cu — geometry experiment for K2b pass 1 (filtered histogram + candidate staging + provisional mask);
+// not product code.  The product kernel is a persistent grid (6 CTAs/SM x 256 threads) because every CTA owns one
+// private staging region; the 2-read/1-write kernels of the path run ~15 % closer to the copy ceiling with small
+// CTAs and a large grid.  Variant B keeps one staging region per SM (indexed by %smid) and reserves space with ONE
+// global atomic per tile, so the grid can be as large as the ratio-mask kernel's.
+//   A : product geometry  — per-CTA region, shared-memory counter, grid = SMs x 6, 256 threads, unroll 4
+//   B : large grid        — per-SM region, per-tile reservation, grid = SMs x 16 x 32 (grid-stride), 128 threads
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/tune/tune_hist1.bin tools/tune/tune_hist1.cu
+// Run  : timeout 60 tools/tune/tune_hist1.bin
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ uint32_t key_of(float x) {
+  uint32_t b = __float_as_uint(x) & 0x7fffffffu;
+  return b > 0x7f800000u ? 0u : b + 1u;
+}
+
+struct RunCache {
+  uint32_t bin = 0xffffffffu, count = 0;
+  __device__ __forceinline__ void push(u64* hist, uint32_t b) {
+    if (b == bin) { ++count; } else { if (count) atomicAdd(hist + bin, (u64)count); bin = b; count = 1; }
+  }
+  __device__ __forceinline__ void flush(u64* hist) { if (count) atomicAdd(hist + bin, (u64)count); count = 0; }
+};
+
+// ---- A: the product kernel's structure --------------------------------------------------------------------
+template <int THREADS, int UNROLL, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS)
+hist1_a(const float4* __restrict__ a4, int64_t nvec, uint32_t prefix, u64* __restrict__ bins, u64* __restrict__ regions,
+        u64 cap, u64* __restrict__ counts, unsigned int* __restrict__ m4) {
+  __shared__ unsigned int s_count;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  u64* region = regions + (u64)blockIdx.x * cap;
+  RunCache rc;
+  const int64_t tile = (int64_t)THREADS * UNROLL, ntiles = (nvec + tile - 1) / tile;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * tile + threadIdx.x;
+    float4 x[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t v = base + (int64_t)u * THREADS;
+      x[u] = v < nvec ? __ldcs(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t v = base + (int64_t)u * THREADS;
+      if (v >= nvec) continue;
+      const uint32_t k[4] = {key_of(x[u].x), key_of(x[u].y), key_of(x[u].z), key_of(x[u].w)};
+      uint32_t packed = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if ((k[q] >> 16) == prefix) {
+          rc.push(bins, k[q] & 0xffffu);
+          const unsigned int pos = atomicAdd(&s_count, 1u);
+          if (pos < cap) region[pos] = ((u64)(v * 4 + q) << 16) | (k[q] & 0xffffu);
+        }
+        packed |= ((k[q] >> 16) > prefix ? 1u : 0u) << (8 * q);
+      }
+      m4[v] = packed;
+    }
+  }
+  rc.flush(bins);
+  __syncthreads();
+  if (threadIdx.x == 0) counts[blockIdx.x] = s_count;
+}
+
+// ---- B: large grid, one region per SM, one reservation per tile ---------------------------------------------
+template <int THREADS, int UNROLL, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS)
+hist1_b(const float4* __restrict__ a4, int64_t nvec, uint32_t prefix, u64* __restrict__ bins, u64* __restrict__ regions,
+        u64 cap, u64* __restrict__ counts, unsigned int* __restrict__ m4) {
+  __shared__ unsigned int s_count;
+  __shared__ u64 s_base;
+  unsigned int smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  u64* region = regions + (u64)smid * cap;
+  RunCache rc;
+  const int64_t tile = (int64_t)THREADS * UNROLL, ntiles = (nvec + tile - 1) / tile;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const int64_t base = t * tile + threadIdx.x;
+    float4 x[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t v = base + (int64_t)u * THREADS;
+      x[u] = v < nvec ? __ldcs(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    u64 mine[4];                       // a thread rarely holds more than a few candidates per tile; extras spill below
+    unsigned int slot[4], nmine = 0;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t v = base + (int64_t)u * THREADS;
+      if (v >= nvec) continue;
+      const uint32_t k[4] = {key_of(x[u].x), key_of(x[u].y), key_of(x[u].z), key_of(x[u].w)};
+      uint32_t packed = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if ((k[q] >> 16) == prefix) {
+          rc.push(bins, k[q] & 0xffffu);
+          const unsigned int pos = atomicAdd(&s_count, 1u);
+          if (nmine < 4) { mine[nmine] = ((u64)(v * 4 + q) << 16) | (k[q] & 0xffffu); slot[nmine] = pos; ++nmine; }
+        }
+        packed |= ((k[q] >> 16) > prefix ? 1u : 0u) << (8 * q);
+      }
+      m4[v] = packed;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = s_count ? atomicAdd(counts + smid, (u64)s_count) : 0ull;
+    __syncthreads();
+    for (unsigned int i = 0; i < nmine; ++i)
+      if (s_base + slot[i] < cap) region[s_base + slot[i]] = mine[i];
+  }
+  rc.flush(bins);
+}
+
+__global__ void fill_normal(float* g, int64_t n, float sigma) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t s = (uint64_t)i * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    float acc = 0.f;
+    for (int k = 0; k < 12; ++k) {       // Irwin-Hall: sum of 12 uniforms - 6 ~ N(0, 1)
+      s ^= s >> 33; s *= 0xff51afd7ed558ccdull; s ^= s >> 29;
+      acc += (float)(s & 0xffffff) * (1.0f / 16777216.0f);
+    }
+    g[i] = (acc - 6.0f) * sigma;
+  }
+}
+
+__global__ void checksum(const unsigned int* m4, int64_t nvec, u64* out) {
+  u64 s = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x)
+    s += __popc(m4[i]);
+  atomicAdd(out, s);
+}
+
+template <typename F>
+static float time_ms(F launch, int iters) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  std::vector<float> t;
+  for (int i = 0; i < iters + 2; ++i) {
+    cudaEventRecord(a);
+    launch();
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms;
+    cudaEventElapsedTime(&ms, a, b);
+    if (i >= 2) t.push_back(ms);
+  }
+  std::sort(t.begin(), t.end());
+  return t[t.size() / 2];
+}
+
+int main() {
+  const int64_t n = 675129632, nvec = n / 4;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  float* g;
+  unsigned int* mask;
+  u64 *bins, *regions, *counts, *sum;
+  const u64 total_cap = (u64)n / 32;
+  cudaMalloc(&g, n * sizeof(float));
+  cudaMalloc(&mask, nvec * sizeof(unsigned int));
+  cudaMalloc(&bins, 65536 * sizeof(u64));
+  cudaMalloc(&regions, total_cap * sizeof(u64));
+  cudaMalloc(&counts, 4096 * sizeof(u64));
+  cudaMalloc(&sum, sizeof(u64));
+  fill_normal<<<sms * 8, 256>>>(g, n, 1e-2f);
+  const float med = 0.6745e-2f;                          // median |x| of N(0, 1e-2): the bin a k = n/2 select lands in
+  uint32_t bits;
+  memcpy(&bits, &med, 4);
+  const uint32_t prefix = (bits + 1u) >> 16;
+  const float4* a4 = reinterpret_cast<const float4*>(g);
+
+  auto run = [&](const char* name, int grid, auto launch) {
+    auto once = [&] {
+      cudaMemsetAsync(bins, 0, 65536 * sizeof(u64));
+      cudaMemsetAsync(counts, 0, 4096 * sizeof(u64));
+      launch();
+    };
+    const float ms = time_ms(once, 9);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("{\"variant\": \"%s\", \"error\": \"%s\"}\n", name, cudaGetErrorString(e)); return; }
+    std::vector<u64> hc(4096), hb(65536);
+    cudaMemcpy(hc.data(), counts, 4096 * sizeof(u64), cudaMemcpyDeviceToHost);
+    cudaMemcpy(hb.data(), bins, 65536 * sizeof(u64), cudaMemcpyDeviceToHost);
+    u64 staged = 0, binned = 0, hs = 0;
+    for (u64 c : hc) staged += c;
+    for (u64 c : hb) binned += c;
+    cudaMemset(sum, 0, 8);
+    checksum<<<sms * 8, 256>>>(mask, nvec, sum);
+    cudaMemcpy(&hs, sum, 8, cudaMemcpyDeviceToHost);
+    printf("{\"variant\": \"%s\", \"grid\": %d, \"ms\": %.4f, \"GBps_5B_per_elem\": %.1f, \"staged\": %llu, \"binned\": %llu, "
+           "\"mask_ones\": %llu}\n", name, grid, ms, n * 5.0 / (ms * 1e-3) / 1e9, staged, binned, hs);
+    fflush(stdout);
+  };
+  {
+    const int grid = sms * 6;
+    run("A per-CTA regions, 256 thr x4, 6 CTAs/SM (product)", grid, [&] {
+      hist1_a<256, 4, 6><<<grid, 256>>>(a4, nvec, prefix, bins, regions, total_cap / grid, counts, mask);
+    });
+  }
+  {
+    const int grid = sms * 16 * 32;
+    run("B per-SM regions, 128 thr x4, grid SMs x 512", grid, [&] {
+      hist1_b<128, 4, 12><<<grid, 128>>>(a4, nvec, prefix, bins, regions, total_cap / 192, counts, mask);
+    });
+  }
+  {
+    const int grid = sms * 16 * 32;
+    run("B per-SM regions, 128 thr x2, grid SMs x 512", grid, [&] {
+      hist1_b<128, 2, 16><<<grid, 128>>>(a4, nvec, prefix, bins, regions, total_cap / 192, counts, mask);
+    });
+  }
+  {
+    const int grid = sms * 8 * 32;
+    run("B per-SM regions, 256 thr x2, grid SMs x 256", grid, [&] {
+      hist1_b<256, 2, 8><<<grid, 256>>>(a4, nvec, prefix, bins, regions, total_cap / 192, counts, mask);
+    });
+  }
+  {
+    const int grid = sms * 6;
+    run("B per-SM regions, 256 thr x4, persistent 6 CTAs/SM", grid, [&] {
+      hist1_b<256, 4, 6><<<grid, 256>>>(a4, nvec, prefix, bins, regions, total_cap / 192, counts, mask);
+    });
+  }
+  return 0;
+}
