@@ -30,7 +30,7 @@ struct RunCache {
 };
 
 // ---- A: the product kernel's structure --------------------------------------------------------------------
-template <int THREADS, int UNROLL, int CTAS>
+template <int THREADS, int UNROLL, int CTAS, bool STCS = false>
 __global__ void __launch_bounds__(THREADS, CTAS)
 hist1_a(const float4* __restrict__ a4, int64_t nvec, uint32_t prefix, u64* __restrict__ bins, u64* __restrict__ regions,
         u64 cap, u64* __restrict__ counts, unsigned int* __restrict__ m4) {
@@ -63,7 +63,7 @@ hist1_a(const float4* __restrict__ a4, int64_t nvec, uint32_t prefix, u64* __res
         }
         packed |= ((k[q] >> 16) > prefix ? 1u : 0u) << (8 * q);
       }
-      m4[v] = packed;
+      if (STCS) __stcs(m4 + v, packed); else m4[v] = packed;
     }
   }
   rc.flush(bins);
@@ -206,6 +206,36 @@ int main() {
     const int grid = sms * 6;
     run("A per-CTA regions, 256 thr x4, 6 CTAs/SM (product)", grid, [&] {
       hist1_a<256, 4, 6><<<grid, 256>>>(a4, nvec, prefix, bins, regions, total_cap / grid, counts, mask);
+    });
+  }
+  {
+    const int grid = sms * 6;
+    run("A2 as A, provisional mask stored with st.global.cs", grid, [&] {
+      hist1_a<256, 4, 6, true><<<grid, 256>>>(a4, nvec, prefix, bins, regions, total_cap / grid, counts, mask);
+    });
+  }
+  {
+    const int grid = sms * 8;
+    run("A3 per-CTA regions, 256 thr x2, 8 CTAs/SM", grid, [&] {
+      hist1_a<256, 2, 8><<<grid, 256>>>(a4, nvec, prefix, bins, regions, total_cap / grid, counts, mask);
+    });
+  }
+  {
+    const int grid = sms * 12;
+    run("A4 per-CTA regions, 128 thr x4, 12 CTAs/SM", grid, [&] {
+      hist1_a<128, 4, 12><<<grid, 128>>>(a4, nvec, prefix, bins, regions, total_cap / grid, counts, mask);
+    });
+  }
+  {
+    const int grid = sms * 3;
+    run("A5 per-CTA regions, 512 thr x4, 3 CTAs/SM", grid, [&] {
+      hist1_a<512, 4, 3><<<grid, 512>>>(a4, nvec, prefix, bins, regions, total_cap / grid, counts, mask);
+    });
+  }
+  {
+    const int grid = sms * 4;
+    run("A6 per-CTA regions, 256 thr x8, 4 CTAs/SM, st.global.cs", grid, [&] {
+      hist1_a<256, 8, 4, true><<<grid, 256>>>(a4, nvec, prefix, bins, regions, total_cap / grid, counts, mask);
     });
   }
   {
