@@ -108,6 +108,47 @@ def _select_protocol(rank, tmp):
         assert torch.equal(two_pass, want), (rank, k)
 
 
+def _bucketed_gradient_exchange(rank, tmp):
+    """BucketedGradReducer == one monolithic all-reduce: the FlatParams constructor needs no GPU (only kernels do), so
+    the hook / bucket logic runs here on CPU tensors with gloo."""
+    import torch.nn as nn
+    from sfron_b200.dist import BucketedGradReducer, ShardGroup
+    from sfron_b200.flat import FlatParams
+    torch.manual_seed(0)                                  # identical weights on both ranks
+    model = nn.Sequential(nn.Linear(7, 33), nn.Tanh(), nn.Linear(33, 19), nn.Tanh(), nn.Linear(19, 5))
+    model[2].bias.requires_grad_(False)                   # a frozen parameter in the middle
+    import copy
+    plain = copy.deepcopy(model)                          # same weights, ordinary per-tensor gradients, no hooks
+    flat = FlatParams(model, torch.device("cpu"))
+    sg = ShardGroup(flat.n)
+    red = BucketedGradReducer(flat, sg, bucket_bytes=200 * 4)
+    assert len(red.buckets) >= 3 and red.buckets[0][0] == 0 and red.buckets[-1][1] == flat.n
+    assert all(a[1] == b[0] for a, b in zip(red.buckets, red.buckets[1:]))
+    for step in range(3):
+        x = torch.randn(4, 7, generator=torch.Generator().manual_seed(10 * step + rank))    # different data per rank
+        def loss_of(m):
+            if step == 2:                                 # a pass that does not reach the first layer's parameters
+                return m[4](torch.tanh(m[2](torch.tanh(x @ torch.ones(7, 33))))).pow(2).sum()
+            return m(x).pow(2).sum()
+
+        plain.zero_grad()
+        loss_of(plain).backward()
+        want = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1)
+                          for p in plain.parameters() if p.requires_grad])
+        dist.all_reduce(want)
+        want /= WORLD
+        flat.zero_grad()
+        loss_of(model).backward()                         # buckets start their all-reduce while this runs
+        shard = red.finish()
+        assert torch.equal(flat.g, want), step
+        assert shard.data_ptr() == flat.g[sg.lo:].data_ptr() and shard.numel() == sg.n_local
+    red.remove()
+
+
+def test_bucketed_gradient_exchange(tmp_path):
+    _spawn("_bucketed_gradient_exchange", tmp_path)
+
+
 def test_shards_and_collectives(tmp_path):
     _spawn("_shards_and_collectives", tmp_path)
 

@@ -137,8 +137,16 @@ def run_ours(args, dev, ac, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    reducer = None
+    if sg is not None and args.dp_exchange == "bucketed":
+        from sfron_b200.dist import BucketedGradReducer
+        assert not args.cuda_graph, "bucketed exchange is an eager-mode option"
+        reducer = BucketedGradReducer(flat, sg, bucket_bytes=args.bucket_mb << 20)
+
     def grads():
         if sg is not None:
+            if reducer is not None:
+                return reducer.finish()                      # buckets were all-reduced while backward was running
             if args.dp_exchange == "allreduce":
                 return sg.reduce_gradients_(flat.g_padded, average=True)[:sg.n_local]
             return sg.reduce_scatter_gradients_(flat.g_padded, average=True)
@@ -253,7 +261,10 @@ def main():
                     help="ours arm only: bf16 working weights / gradients with fp32 master + state (BASELINE config 3)")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="ours arm: capture the whole forget iteration (collectives included) in a CUDA graph and replay it")
-    ap.add_argument("--dp-exchange", default="reduce_scatter", choices=["reduce_scatter", "allreduce"])
+    ap.add_argument("--dp-exchange", default="reduce_scatter", choices=["reduce_scatter", "allreduce", "bucketed"],
+                    help="bucketed: all-reduce in buckets started from autograd hooks while backward still runs "
+                         "(sfron_b200.dist.BucketedGradReducer; correctness covered by the gloo test, not yet timed on GPUs)")
+    ap.add_argument("--bucket-mb", type=int, default=64)
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

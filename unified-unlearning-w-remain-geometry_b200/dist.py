@@ -8,6 +8,7 @@ inside torch on GPU 0.  Here:
   * the only data-path collectives are
       - gradients: all-reduce (replicated update) or reduce-scatter (sharded update) of the flat
         gradient produced by each rank's backward pass               -> `reduce_gradients_`
+        (`BucketedGradReducer`: the same all-reduce cut into buckets that start while backward still runs)
       - clip norm: all-reduce of ONE double (the masked sum of squares) -> `reduce_scalar_`
       - top-k select: all-reduce of the histogram bins (256 KB, then 512 KB) and an all-gather of
         one tie count per rank                                        -> `reduce_bins_`, `tie_base_`
@@ -136,6 +137,77 @@ class ShardGroup:
             for r, s in enumerate(shards):
                 if s.numel():
                     dist.broadcast(s, src=dist.get_global_rank(self.group, r) if self.group else r, group=self.group)
+
+
+class BucketedGradReducer:
+    """Overlaps the data-parallel gradient exchange with the backward pass.
+
+    `FlatParams` makes every `param.grad` a view of the flat gradient `g`, and autograd produces gradients roughly in
+    reverse parameter order, so the tail of `g` is final long before the head.  The flat vector is cut into contiguous
+    buckets (whole parameters, ~`bucket_bytes` each); a post-accumulate-grad hook counts the parameters of each bucket
+    and, when a bucket is complete, starts its all-reduce asynchronously (NCCL runs it on its own stream while the rest
+    of the backward pass keeps the SMs busy).  `finish()` waits for every bucket and returns this rank's shard, exactly
+    what `ShardGroup.reduce_gradients_` returns after a monolithic all-reduce (same sums: every element is reduced once).
+
+    One backward pass per `finish()`; parameters that receive no gradient in a pass (their hook never fires) are
+    reduced by `finish()` with whatever their bucket holds (zeros after `zero_grad`).
+    """
+
+    def __init__(self, flat, shards: ShardGroup, bucket_bytes: int = 64 << 20, average: bool = True):
+        self.flat, self.shards, self.average = flat, shards, average
+        elem = flat.g.element_size()
+        self.buckets: List[Tuple[int, int]] = []            # [lo, hi) element ranges, in flat order
+        self._bucket_of: List[int] = []                      # per trainable parameter (layout order)
+        lo = 0
+        for seg in flat.layout:
+            end = seg.offset + seg.numel
+            self._bucket_of.append(len(self.buckets))
+            if (end - lo) * elem >= bucket_bytes:
+                self.buckets.append((lo, end))
+                lo = end
+        if lo < flat.n or not self.buckets:
+            self.buckets.append((lo, flat.n))
+        self._bucket_of = [min(b, len(self.buckets) - 1) for b in self._bucket_of]
+        self._need = [0] * len(self.buckets)
+        for b in self._bucket_of:
+            self._need[b] += 1
+        self._seen = [0] * len(self.buckets)
+        self._work: List[Optional[object]] = [None] * len(self.buckets)
+        self._handles = [prm.register_post_accumulate_grad_hook(self._make_hook(b))
+                         for prm, b in zip(flat._train_params, self._bucket_of)]
+
+    def _make_hook(self, bucket: int):
+        def hook(_param):
+            self._seen[bucket] += 1
+            if self._seen[bucket] == self._need[bucket]:
+                self._launch(bucket)
+        return hook
+
+    def _launch(self, bucket: int) -> None:
+        lo, hi = self.buckets[bucket]
+        view = self.flat.g[lo:hi]
+        if self.average and self.shards._nccl:
+            self._work[bucket] = dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.shards.group, async_op=True)
+        else:
+            self._work[bucket] = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.shards.group, async_op=True)
+
+    def finish(self) -> torch.Tensor:
+        """Call after `loss.backward()`: completes the exchange and returns this rank's gradient shard."""
+        for b in range(len(self.buckets)):
+            if self._work[b] is None:                        # a parameter of this bucket got no gradient this pass
+                self._launch(b)
+        for b, w in enumerate(self._work):
+            w.wait()
+            self._work[b] = None
+            self._seen[b] = 0
+        if self.average and not self.shards._nccl:
+            self.flat.g.div_(self.shards.world)
+        return self.shards.local(self.flat.g)
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
 
 
 # byte offset of sfr_select_state.thr_key: 5 x u64 (k, k_in_bin, count_gt, count_eq, tie_budget) + u32 prefix
