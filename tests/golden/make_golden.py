@@ -496,6 +496,73 @@ def ddpm_runner():
     print("wrote ddpm runner: N =", theta0.numel(), "fisher grads", nf + nr, "sfron records", 2 * n_iters)
 
 
+def ddpm_sa():
+    """Diffusion.sa_forget (Selective Amnesia, DDPM/runners/diffusion.py:354-470) executed whole: the EWC penalty
+    `lmbda * sum(F * (p - p_mle)**2)` the reference builds per tensor per step (:424-433), its backward, clip, Adam, EMA.
+    The diffusion loss itself (out of scope, and inseparable from the penalty inside one backward) is replaced by a
+    LINEAR function of the parameters, sum <p, c>, whose gradient is the constant c: the recorded total gradient is then
+    (1 + gamma) * c + d(penalty)/dp with both terms known."""
+    import pickle
+    sys.path.insert(0, os.path.join(REF, "DDPM"))
+    import runners.diffusion as RD
+
+    def d2n(d):
+        ns = argparse.Namespace()
+        for k, v in d.items():
+            setattr(ns, k, d2n(v) if isinstance(v, dict) else v)
+        return ns
+
+    cfg = yaml.safe_load(open(os.path.join(REF, "DDPM/configs/cifar10_sfron.yml")))
+    cfg["data"]["image_size"] = 8
+    n_iters, gamma, lmbda = 4, 0.5, 40.0
+    cfg["training"].update(n_iters=n_iters, snapshot_freq=n_iters, log_freq=10 ** 9, gamma=gamma, lmbda=lmbda)
+    config = d2n(cfg)
+    from torch.utils.data import DataLoader, TensorDataset
+    g = torch.Generator().manual_seed(61)
+    loader = DataLoader(TensorDataset(torch.rand(6, 3, 8, 8, generator=g), torch.randint(1, 10, (6,), generator=g)),
+                        batch_size=3, shuffle=False)
+    torch.manual_seed(60)
+    init = nn.DataParallel(TinyCond(config))
+    names = [n for n, _ in init.named_parameters()]
+    shapes = {n: list(p.shape) for n, p in init.named_parameters()}
+    consts = {n: torch.randn(p.shape, generator=g) * 2e-3 for n, p in init.named_parameters()}
+    fisher = {n: torch.rand(p.shape, generator=g) * 3.0 for n, p in init.named_parameters()}
+
+    def linear_loss(model, x0, t, c, e, b, cond_drop_prob=0.1, keepdim=False):
+        return sum((p * consts[n]).sum() for n, p in model.named_parameters())
+
+    RD.all_but_one_class_path_dataset = lambda config, path, label: loader
+    RD.Conditional_Model = TinyCond
+    RD.loss_registry_conditional = {"simple": linear_loss}
+    RD.Diffusion.sample_visualization = lambda self, *a, **k: None
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "ckpts"))
+        from models.ema import EMAHelper
+        ema0 = EMAHelper(mu=config.model.ema_rate)
+        ema0.register(init)
+        torch.save([init.state_dict(), {}, 0, ema0.state_dict()], os.path.join(tmp, "ckpts/ckpt.pth"))
+        with open(os.path.join(tmp, "fisher_dict.pkl"), "wb") as f:
+            pickle.dump(fisher, f)
+        config.ckpt_dir = os.path.join(tmp, "out")
+        os.makedirs(config.ckpt_dir)
+        args = argparse.Namespace(ckpt_folder=tmp, label_to_forget=0, cond_scale=2.0)
+        TinyCond.instances.clear()
+        torch.manual_seed(62)
+        with BackwardRecorder() as rec:
+            RD.Diffusion(args, config).sa_forget()
+        assert len(rec.records) == n_iters
+        model_sd, opt_sd, step, ema_sd = torch.load(os.path.join(config.ckpt_dir, "ckpt.pth"), weights_only=False)
+    fixture = dict(names=names, shapes=shapes, theta0=flat(init.parameters()), grads=torch.stack(rec.records),
+                   base_grad=flat([consts[n] for n in names]) * (1 + gamma), base_terms=(1.0, gamma),
+                   consts=flat([consts[n] for n in names]), fisher=flat([fisher[n] for n in names]),
+                   theta=flat([model_sd[n] for n in names]), ema=flat([ema_sd[n[len("module."):]] for n in names]),
+                   hyper=dict(lr=config.optim.lr, beta1=config.optim.beta1, beta2=0.999, eps=config.optim.eps,
+                              weight_decay=config.optim.weight_decay, grad_clip=config.optim.grad_clip,
+                              ema_rate=config.model.ema_rate, n_iters=n_iters, gamma=gamma, lmbda=lmbda))
+    torch.save(fixture, os.path.join(OUT, "ddpm_sa_forget.pt"))
+    print("wrote ddpm sa_forget: grad norms", fixture["grads"].norm(dim=1).tolist())
+
+
 class TinyDiT(nn.Module):
     def __init__(self):
         super().__init__()
@@ -957,6 +1024,7 @@ PARTS = {
     "dit_mask": dit_masks,
     "ddpm_loop": ddpm_loop,
     "ddpm_runner": ddpm_runner,
+    "ddpm_sa": ddpm_sa,
     "dit_loop": dit_loop,
     "dit_scripts": dit_scripts,
     "sd_scripts": sd_scripts,

@@ -390,6 +390,30 @@ def test_sd_scripts_dropin_against_whole_reference_scripts(dev, tmp_path):
     assert list(sd.keys()) == names                                            # plain state_dict, as save_model writes
 
 
+def test_ddpm_sa_forget_ewc_dropin(dev):
+    """Selective-Amnesia step of the DDPM runner executed whole (fixture ddpm_sa_forget.pt): base-loss backward, then
+    `add_ewc_penalty` (fused penalty + gradient kernel) instead of the per-tensor penalty graph, clip, Adam, EMA."""
+    from sfron_b200.methods.diffusion import DiffusionUnlearner
+    fx = load_golden("ddpm_sa_forget.pt")
+    h, pnames = fx["hyper"], fx["names"]
+    names = [n[len("module."):] for n in pnames]
+    shapes = {k[len("module."):]: v for k, v in fx["shapes"].items()}
+    model = TinyCond()
+    set_flat(model, fx["theta0"], names, shapes)
+    un = DiffusionUnlearner(model.to(dev), "ddpm", lr=h["lr"])
+    un.snapshot_params("params_mle")                                   # params_mle_dict[name] = param.data.clone()
+    un.mhp.hp.set_buffer("fim", fx["fisher"].to(dev))                  # fisher_dict.pkl
+    un.mhp.zero_grad()
+    for step, g_ref in enumerate(fx["grads"]):
+        inject(un.model, fx["base_grad"]).backward()                   # (1 + gamma) * c: the stand-in diffusion loss
+        penalty = un.add_ewc_penalty(h["lmbda"])
+        assert (float(penalty) == 0.0) == (step == 0)
+        assert close(un.mhp.grads(), g_ref), step                      # == what the reference's single backward produced
+        un.mhp.joint_step(use_mask=False, max_norm=h["grad_clip"], ema=True)
+    assert close(torch.cat([p.detach().reshape(-1) for p in un.model.parameters()]), fx["theta"])
+    assert close(torch.cat([un.mhp.slow_state_dict()["module." + n].reshape(-1) for n in names]), fx["ema"])
+
+
 def test_bf16_model_mixed_precision_flat_params(dev):
     """BASELINE config 3 (bf16): module weights / grads are bf16 views, the kernels keep an fp32 master."""
     import sfron_b200 as sfr

@@ -267,3 +267,25 @@ def test_sd_scripts_executed_whole():
     for g in rec["grads"]:
         loop.forget_step(unflat(g, names, shapes), mask=masks)
     assert _close(loop.flat("p"), rec["theta"])
+
+
+def test_ddpm_sa_forget_ewc_penalty_executed_whole():
+    """Diffusion.sa_forget executed whole (fixture ddpm_sa_forget.pt): the per-step gradient the reference's backward
+    produced equals (1 + gamma) * c (the linear stand-in loss) + the EWC gradient of `lmbda * sum(F * (p - p_mle)**2)`
+    as the oracle forms it (runners/diffusion.py:424-433), and clip -> Adam -> EMA reproduce the saved checkpoint."""
+    fx = load_golden("ddpm_sa_forget.pt")
+    names, shapes, hp = fx["names"], fx["shapes"], fx["hyper"]
+    theta0 = unflat(fx["theta0"], names, shapes)
+    fisher = unflat(fx["fisher"], names, shapes)
+    loop = O.FlatReferenceLoop(shapes, theta0, "adam", dict(lr=hp["lr"], beta1=hp["beta1"], beta2=hp["beta2"], eps=hp["eps"],
+                                                            weight_decay=hp["weight_decay"]), ema_mode="ddpm", ema_a=hp["ema_rate"])
+    for step, g_ref in enumerate(fx["grads"]):
+        ewc, penalty = O.ewc_penalty_grads({n: p.detach() for n, p in loop.params.items()}, theta0, fisher, hp["lmbda"])
+        total = fx["base_grad"] + torch.cat([ewc[n].reshape(-1) for n in names])
+        if step == 0:
+            assert float(penalty) == 0.0                       # theta == theta_mle: only the base term moves it
+        rms = g_ref.double().pow(2).mean().sqrt()
+        assert bool(((total.double() - g_ref.double()).abs() <= 1e-6 * (g_ref.double().abs() + rms)).all()), step
+        loop.forget_step(unflat(total, names, shapes), mask=None, max_norm=hp["grad_clip"])
+        loop.slow_update()
+    assert _close(loop.flat("p"), fx["theta"]) and _close(loop.flat("slow"), fx["ema"])
