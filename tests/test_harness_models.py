@@ -127,3 +127,25 @@ def test_dit_harness_structure_matches_reference_class():
         full = DiTXL2Harness()
     assert sum(p.numel() for p in full.parameters()) == 675_129_632 and len(list(full.parameters())) == 292
     assert sum(p.numel() for p in full.parameters() if p.requires_grad) == 674_834_720
+
+
+def test_resnet18_harness_counts():
+    from resnet18_cifar import ResNet18Harness
+    m = ResNet18Harness()
+    assert len(_sig(m)) == 62 and sum(p.numel() for p in m.parameters()) == 11_173_962
+
+
+@needs_ref
+def test_resnet18_harness_matches_reference_module():
+    import importlib.util
+    from resnet18_cifar import ResNet18Harness
+    spec = importlib.util.spec_from_file_location("ref_resnet", os.path.join(REF, "Classification/models/resnet.py"))
+    ref_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_mod)
+    torch.manual_seed(0)
+    ref, ours = ref_mod.ResNet18(10).eval(), ResNet18Harness().eval()
+    assert _sig(ours) == _sig(ref)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    x = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        assert torch.allclose(ref(x), ours(x), rtol=1e-5, atol=1e-5)

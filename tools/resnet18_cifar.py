@@ -1,7 +1,7 @@
 """Bench / test HARNESS model: a CIFAR-style ResNet-18 in plain PyTorch (not product code).
 
-Same parameter count and tensor count as the reference's Classification/models/resnet.py ResNet18
-(11,173,962 parameters in 62 tensors): 3x3 stem, four stages of two basic blocks
+Same state-dict names, shapes, order and counts as the reference's Classification/models/resnet.py ResNet18
+(11,173,962 parameters in 62 tensors; checked by tests/test_harness_models.py): 3x3 stem, four stages of two basic blocks
 (64-128-256-512), 1x1 projection shortcuts where the shape changes, global average pool, 10-way
 classifier.  Written for the end-to-end measurement of BASELINE config 1; the forward/backward of
 the reference's models stays in PyTorch and is outside the hot path's scope.
@@ -32,16 +32,15 @@ class ResNet18Harness(nn.Module):
         super().__init__()
         self.conv1 = nn.Conv2d(3, 64, 3, 1, 1, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
-        layers, cin = [], 64
-        for cout, stride in ((64, 1), (128, 2), (256, 2), (512, 2)):
-            layers += [_Block(cin, cout, stride), _Block(cout, cout, 1)]
+        cin = 64
+        for i, (cout, stride) in enumerate(((64, 1), (128, 2), (256, 2), (512, 2)), start=1):
+            setattr(self, f"layer{i}", nn.Sequential(_Block(cin, cout, stride), _Block(cout, cout, 1)))
             cin = cout
-        self.layers = nn.Sequential(*layers)
         self.linear = nn.Linear(512, num_classes)
 
     def forward(self, x):
         x = F.relu(self.bn1(self.conv1(x)))
-        x = self.layers(x)
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.linear(F.adaptive_avg_pool2d(x, 1).flatten(1))
 
 
