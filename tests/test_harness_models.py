@@ -149,3 +149,41 @@ def test_resnet18_harness_matches_reference_module():
     x = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(1))
     with torch.no_grad():
         assert torch.allclose(ref(x), ours(x), rtol=1e-5, atol=1e-5)
+
+
+@needs_ref
+def test_dit_harness_matches_reference_class_outputs():
+    """The reference's own `DiT` class (DiT/models.py) needs timm's PatchEmbed / Attention / Mlp; with the stand-ins
+    that tests/golden/make_golden.py uses for them, a 2-block model of both implementations agrees on names, shapes,
+    order and — same weights — outputs (embedders, adaLN modulation, final layer, unpatchify, fixed pos_embed)."""
+    import importlib.util
+    from dit_xl2 import DiTXL2Harness
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    before = set(sys.modules)
+    saved_models = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "models" or k.startswith("models.")}
+    sys.path.insert(0, os.path.join(REF, "DiT"))
+    try:
+        mg._install_dit_stubs()
+        import models as ref_models
+        torch.manual_seed(0)
+        ref = ref_models.DiT(input_size=8, patch_size=2, hidden_size=32, depth=2, num_heads=4, num_classes=10)
+        with torch.no_grad():
+            for p in ref.parameters():
+                if p.requires_grad and not p.any():
+                    p.normal_(std=0.05)                  # adaLN / final layers are zero-initialised
+        ours = DiTXL2Harness(input_size=8, patch=2, width=32, depth=2, heads=4, classes=10)
+        assert _sig(ours) == _sig(ref)
+        ours.load_state_dict(ref.state_dict(), strict=True)
+        ref.eval(), ours.eval()
+        g = torch.Generator().manual_seed(1)
+        x, t, y = torch.randn(3, 4, 8, 8, generator=g), torch.tensor([0, 500, 999]), torch.tensor([1, 7, 10])
+        with torch.no_grad():
+            a, b = ref(x, t, y), ours(x, t, y)
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), (a - b).abs().max()
+    finally:
+        sys.path.remove(os.path.join(REF, "DiT"))
+        for k in set(sys.modules) - before:
+            del sys.modules[k]
+        sys.modules.update(saved_models)
