@@ -14,6 +14,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (sm_100) GPU; run with `-m gpu` under gpurun")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _library_is_built():
+    """A fresh checkout has no libsfron_b200.so (build artefacts are git-ignored): build it before the first test if
+    the sources changed or it is missing (nvcc cross-compiles without a GPU; a no-op when the stamp matches)."""
+    import __graft_entry__ as entry
+    builder = entry._load_build_module()
+    if not builder.is_fresh():
+        builder.build()
+    yield
+
+
 def load_golden(name):
     return torch.load(os.path.join(GOLDEN, name), weights_only=False)
 
