@@ -563,6 +563,60 @@ def ddpm_sa():
     print("wrote ddpm sa_forget: grad norms", fixture["grads"].norm(dim=1).tolist())
 
 
+def ddpm_fim():
+    """Diffusion.save_fim (entry DDPM/fim.py:84-89; runners/diffusion.py:262-352) executed whole: per-sample gradients
+    summed over all timesteps in chunks (`loss[i].backward(retain_graph=True)`), then F += tmp_i**2 / |D| per sample.
+    Shims: 2 "GPUs" (the batch size is torch.cuda.device_count()), a synthetic ImageFolder, the 411-parameter network,
+    40 diffusion timesteps instead of 1000."""
+    import pickle
+    sys.path.insert(0, os.path.join(REF, "DDPM"))
+    import runners.diffusion as RD
+
+    def d2n(d):
+        ns = argparse.Namespace()
+        for k, v in d.items():
+            setattr(ns, k, d2n(v) if isinstance(v, dict) else v)
+        return ns
+
+    cfg = yaml.safe_load(open(os.path.join(REF, "DDPM/configs/cifar10_sfron.yml")))
+    cfg["data"].update(image_size=8, num_workers=0)
+    cfg["diffusion"]["num_diffusion_timesteps"] = 40
+    cfg["training"].update(save_freq=10 ** 9)
+    config = d2n(cfg)
+    from torch.utils.data import TensorDataset
+    g = torch.Generator().manual_seed(71)
+    data = TensorDataset(torch.rand(4, 3, 8, 8, generator=g), torch.randint(0, 10, (4,), generator=g))
+    bs, n_chunks = 2, 3
+    RD.ImageFolder = lambda path, transform=None: data
+    RD.Conditional_Model = TinyCond
+    orig_count = torch.cuda.device_count
+    torch.cuda.device_count = lambda: bs
+    torch.manual_seed(70)
+    init = nn.DataParallel(TinyCond(config))
+    names = [n for n, _ in init.named_parameters()]
+    shapes = {n: list(p.shape) for n, p in init.named_parameters()}
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            os.makedirs(os.path.join(tmp, "ckpts"))
+            torch.save([init.state_dict(), {}, 0, {}], os.path.join(tmp, "ckpts/ckpt.pth"))
+            args = argparse.Namespace(ckpt_folder=tmp, n_chunks=n_chunks)
+            TinyCond.instances.clear()
+            torch.manual_seed(72)
+            with BackwardRecorder() as rec:
+                RD.Diffusion(args, config).save_fim()
+            with open(os.path.join(tmp, "fisher_dict.pkl"), "rb") as f:
+                fim = pickle.load(f)
+    finally:
+        torch.cuda.device_count = orig_count
+    n_batches = len(data) // bs
+    assert len(rec.records) == n_batches * n_chunks * bs and list(fim.keys()) == names
+    grads = torch.stack(rec.records).reshape(n_batches, n_chunks, bs, -1)          # record order: batch, chunk, sample
+    fixture = dict(names=names, shapes=shapes, chunk_grads=grads, dataset_len=len(data),
+                   fim=flat([fim[n] for n in names]))
+    torch.save(fixture, os.path.join(OUT, "ddpm_fim.pt"))
+    print("wrote ddpm fim: records", len(rec.records), "fim sum", float(fixture["fim"].sum()))
+
+
 class TinyDiT(nn.Module):
     def __init__(self):
         super().__init__()
@@ -1025,6 +1079,7 @@ PARTS = {
     "ddpm_loop": ddpm_loop,
     "ddpm_runner": ddpm_runner,
     "ddpm_sa": ddpm_sa,
+    "ddpm_fim": ddpm_fim,
     "dit_loop": dit_loop,
     "dit_scripts": dit_scripts,
     "sd_scripts": sd_scripts,

@@ -289,3 +289,18 @@ def test_ddpm_sa_forget_ewc_penalty_executed_whole():
         loop.forget_step(unflat(total, names, shapes), mask=None, max_norm=hp["grad_clip"])
         loop.slow_update()
     assert _close(loop.flat("p"), fx["theta"]) and _close(loop.flat("slow"), fx["ema"])
+
+
+def test_ddpm_save_fim_executed_whole():
+    """Diffusion.save_fim executed whole (fixture ddpm_fim.pt): per-sample gradients accumulated over the timestep
+    chunks, then `F[name] += tmp_i[name]**2 / |D|` sample by sample, batch by batch (runners/diffusion.py:326-344)."""
+    fx = load_golden("ddpm_fim.pt")
+    names, shapes = fx["names"], fx["shapes"]
+    acc = {n: torch.zeros(shapes[n]) for n in names}
+    for batch in fx["chunk_grads"]:                            # [n_chunks, bs, n]
+        rows = torch.zeros_like(batch[0])
+        for chunk in batch:                                    # fisher_dict_temp_list[i][name] += param.grad.data
+            rows = rows + chunk
+        O.per_sample_fim(acc, [unflat(r, names, shapes) for r in rows], fx["dataset_len"])
+    got = torch.cat([acc[n].reshape(-1) for n in names])
+    assert bits_equal(got, fx["fim"])
