@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SFR_ABI_VERSION 2
+#define SFR_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SFR_API __attribute__((visibility("default")))
@@ -295,6 +295,87 @@ SFR_API int sfr_soft_threshold(float* p, const float* p0, int64_t n, const float
 SFR_API int sfr_gather_segments(float* flat, const void* const* srcs_dev,
                         const int64_t* offsets_dev, const int64_t* sizes_dev,
                         int32_t count, int src_dtype, int64_t total, sfr_stream_t stream);
+
+/* ===========================================================================
+ * Cross-GPU exchange fused with the kernels it feeds (one process per GPU, NVLink peer memory)
+ * replaces  torch.nn.DataParallel's reduce_add of the per-GPU gradients onto GPU 0 and its weight
+ *           re-broadcast before the next forward
+ *   DiT/forget.py:193,285-322 ; DiT/generate_fisher.py:173,216-291 ;
+ *   DDPM/runners/diffusion.py:110,1060,1126-1180,1270-1281
+ * The flat vector is sharded: rank r owns elements [lo, lo + n_local), lo a multiple of 16.
+ *
+ * sfr_peer_buf describes ONE symmetric buffer as this rank sees it: ptrs[r] is the device address at
+ * which rank r's copy of the buffer is mapped into THIS process (ptrs[rank] is the local copy), and
+ * `multicast` is the NVLS multicast address of the same buffer (NULL if the fabric has none).  The
+ * caller obtains them from its allocator (torch.distributed._symmetric_memory, cuMem* + cuMulticast*,
+ * or cudaIpc*); the library only dereferences them.  Transport per call:
+ *   SFR_XP_P2P       loads from / stores to the `world` mapped pointers; gradients are summed in rank
+ *                    order 0..world-1 in fp32 (deterministic: equals a sequential sum)
+ *   SFR_XP_MULTIMEM  multimem.ld_reduce / multimem.st on the multicast address: the NVSwitch sums the
+ *                    gradients (fp32 accumulation; bf16 results are rounded to bf16) and replicates the
+ *                    weight stores
+ * `average` != 0 divides the sum by `world` (true division), the mean DataParallel's loss takes over
+ * the global batch.
+ *
+ * Ordering is the caller's: sfr_peer_barrier on the same stream before the first kernel that reads
+ * peer gradients (every rank has finished writing them) and after the last kernel that reads them or
+ * pushes weights (nobody overwrites a gradient that is still being read; every weight store has landed).
+ * ======================================================================== */
+#define SFR_MAX_PEERS 8
+#define SFR_XP_P2P 1
+#define SFR_XP_MULTIMEM 2
+
+typedef struct sfr_peer_buf {
+  void* ptrs[SFR_MAX_PEERS];
+  void* multicast;
+} sfr_peer_buf;
+
+typedef struct sfr_peer_geom {
+  int32_t world;
+  int32_t rank;
+  int64_t lo;      /* first element of this rank's shard in the full vector (multiple of 16) */
+  int64_t n_local; /* elements in this rank's shard (ragged only at the end of the vector)   */
+} sfr_peer_geom;
+
+/* Cross-GPU barrier on `stream`, which also all-reduces up to 8 doubles: every rank contributes
+ * vals_dev[0..nvals) and receives in sums_dev[j] the sum over ranks IN RANK ORDER (identical bits on
+ * every rank) — the clip norm's all-reduce (one double) costs no extra launch.
+ * `pad`: a symmetric buffer of sfr_peer_pad_bytes() bytes, zero-filled on every rank before first use and
+ * used by ONE stream at a time.  The epoch lives in the pad, so captured launches replay correctly.
+ * A rank that waits longer than timeout_ns (0 = 30 s) sets word 1 of its pad (u64) to 1 and returns:
+ * the caller checks that status; the GPU never hangs on a dead peer. */
+SFR_API int64_t sfr_peer_pad_bytes(void);
+SFR_API int sfr_peer_barrier(const sfr_peer_buf* pad, int world, int rank, const double* vals_dev,
+                     double* sums_dev, int nvals, uint64_t timeout_ns, sfr_stream_t stream);
+
+/* Reduce-scatter fused with K1 and the clip norm.  g: every rank's FULL flat gradient (dtype g_dtype).
+ * For this rank's shard, gbar = sum_r g_r [/ world], then any of (NULL = skip):
+ *   g_red[i]      = gbar[i]                                (fp32 reduced shard, local, n_local elements)
+ *   fisher_acc[i] += gbar[i]**2 / fisher_divisor           (K1; same rounding sequence as sfr_fisher_accum)
+ *   *sumsq        += sum_i (gbar[i] * mask[i])**2          (mask may be NULL; same as sfr_masked_sumsq)
+ * mask / g_red / fisher_acc are LOCAL shard pointers (element 0 = vector element lo). */
+SFR_API int sfr_peer_reduce(const sfr_peer_buf* g, int g_dtype, const sfr_peer_geom* geom, int transport,
+                    int average, float* g_red, const uint8_t* mask, double* sumsq,
+                    float* fisher_acc, float fisher_divisor, sfr_stream_t stream);
+
+/* K3 on this rank's shard with the exchange on both sides.  Gradient source: `g_red` (local fp32 shard
+ * left by sfr_peer_reduce — the clipped steps, whose norm must be known first) or, when g != NULL, the
+ * peers' full gradients reduced on the fly (g_transport, average).  p / m / v / mask / ema are local
+ * shard pointers.  Every updated weight is also pushed into all ranks' full-vector buffers: bc_f32
+ * (fp32 weights; NULL = none) and/or bc_bf16 (bf16 working copy; NULL = none) via bc_transport.
+ * args->flags: SFR_F_MASK | SFR_F_MASK_AFTER_CLIP | SFR_F_SGD_FIRST_STEP only.  Everything else as
+ * sfr_fused_update (same arithmetic: the two share their per-element code). */
+SFR_API int sfr_peer_fused_update(float* p, const float* g_red, const sfr_peer_buf* g, int g_dtype,
+                    int g_transport, int average, float* m, float* v, const uint8_t* mask,
+                    float* ema, const sfr_peer_buf* bc_f32, const sfr_peer_buf* bc_bf16,
+                    int bc_transport, const sfr_peer_geom* geom, const sfr_update_args* args,
+                    const double* clip_sumsq, long long* step_counter_dev,
+                    void* consts_scratch_dev, sfr_stream_t stream);
+
+/* All-gather alone: push this rank's shard (src_local, n_local elements of elem_bytes = 2 | 4) into every
+ * rank's full-vector buffer `dst` at element offset lo. */
+SFR_API int sfr_peer_broadcast(const void* src_local, const sfr_peer_buf* dst, int elem_bytes,
+                    const sfr_peer_geom* geom, int transport, sfr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -284,6 +284,23 @@ class FlatReferenceLoop:
         return torch.cat([st[p][key].detach().flatten() for p in self.params.values()])
 
 
+# --------------------------------------------------------------------------- data-parallel gradient
+def dp_reduce(grads: Sequence[Tensor], average: bool = True) -> Tensor:
+    """The gradient a data-parallel step updates with, from the per-replica gradients.
+
+    The reference wraps its models in `torch.nn.DataParallel` (DiT/forget.py:193, DiT/generate_fisher.py:173,
+    DDPM/runners/diffusion.py:110,1060): backward of the replicated module ends in `ReduceAddCoalesced`
+    (torch/nn/parallel/_functions.py), i.e. `comm.reduce_add`, which starts from the first replica's gradient and
+    adds the others IN DEVICE ORDER.  With one process per GPU each rank's loss is the mean over its own batch,
+    so the global-batch mean is that sum divided by the number of ranks (`average`)."""
+    total = grads[0].detach().clone().float()
+    for g in grads[1:]:
+        total.add_(g.detach().float())
+    if average:
+        total = total / len(grads)
+    return total
+
+
 # --------------------------------------------------------------------------- flat reference-form ops
 # The stock-torch op sequences of SURVEY.md §2.1 on ONE flat vector: the form timed as the
 # CPU baseline (bench.py) and used for size-independent parity checks in the sweep.

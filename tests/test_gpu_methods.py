@@ -429,6 +429,7 @@ def test_bf16_model_mixed_precision_flat_params(dev):
     n = fp.n
     ref = O.FlatReferenceLoop({"w": (n,)}, {"w": theta0}, "adamw", dict(lr=1e-3), ema_mode="dit", ema_a=0.999)
     mhp.hp.mask.fill_(1)
+    mhp.hp.mark_mask_ready()
     g = torch.Generator().manual_seed(1)
     for _ in range(3):
         grad = (torch.randn(n, generator=g) * 0.1).bfloat16()

@@ -129,6 +129,7 @@ def run_ours(args, dev, ac, rank, world):
     hp.init_slow(p_loc)
     frozen_slow = flat.frozen.clone()
     hp.mask.copy_((torch.rand(hi - lo, device=dev, generator=gen) < 0.5).to(torch.uint8))
+    hp.mark_mask_ready()
     model.train()
     res = {}
 

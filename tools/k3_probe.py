@@ -9,7 +9,7 @@ gen = torch.Generator(device=dev).manual_seed(0)
 hp = sfr.HotPath(n, dev, sfr.OptConfig(kind="adamw", lr=1e-4), ema_mode="dit", ema_a=0.9999)
 p = torch.empty(n, device=dev).normal_(0, 0.02, generator=gen)
 g = torch.empty(n, device=dev).normal_(0, 1e-2, generator=gen)
-hp.init_slow(p); hp.mask.copy_((torch.rand(n, device=dev, generator=gen) < 0.5).to(torch.uint8))
+hp.init_slow(p); hp.mask.copy_((torch.rand(n, device=dev, generator=gen) < 0.5).to(torch.uint8)); hp.mark_mask_ready()
 hp.remain_step(p, g, ema=False)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 hp.sumsq.fill_(float(n) * 1e-4 * 0.5)

@@ -19,13 +19,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsfron_b200.so")
 
 # ---- constants mirrored from include/sfron_b200.h ---------------------------------------
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, ERR_NULL, ERR_ALIGN, ERR_ARG, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 F32, BF16 = 0, 1
 KEY_ABS, KEY_RATIO, KEY_ABSDIFF = 0, 1, 2
 SELECT_BINS0, SELECT_BINS1 = 32768, 65536
 SELECT_BINS_ALLOC = 65536 + 128         # u64 words of a bins buffer (histogram + the scan's partials / ticket)
 MAX_THRESHOLDS = 8
+MAX_PEERS = 8
+XP_P2P, XP_MULTIMEM = 1, 2
 OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2
 EMA_NONE, EMA_DDPM, EMA_DIT, EMA_SLOWFAST = 0, 1, 2, 3
 F_MASK, F_MASK_AFTER_CLIP, F_ZERO_GRAD, F_SGD_FIRST_STEP, F_WRITE_BF16 = 1, 2, 4, 8, 16
@@ -36,6 +38,7 @@ EXPORTED_SYMBOLS = (
     "sfr_select_scan", "sfr_select_scratch_elems", "sfr_select_apply", "sfr_masked_sumsq",
     "sfr_fused_update", "sfr_ema_update", "sfr_gather_segments",
     "sfr_ewc_penalty", "sfr_select_threshold_value", "sfr_soft_threshold",
+    "sfr_peer_pad_bytes", "sfr_peer_barrier", "sfr_peer_reduce", "sfr_peer_fused_update", "sfr_peer_broadcast",
 )
 
 
@@ -43,6 +46,7 @@ class SfrError(RuntimeError):
     def __init__(self, code: int, where: str, message: str):
         super().__init__(f"{where}: {message} (code {code})")
         self.code = code
+        _seen_devices.clear()          # a wrapper that fails half-way leaves no device record behind
 
 
 class UpdateArgs(C.Structure):
@@ -64,6 +68,16 @@ class SelectState(C.Structure):
         ("prefix", C.c_uint32), ("thr_key", C.c_uint32), ("select_all", C.c_uint32),
         ("select_none", C.c_uint32), ("reserved", C.c_ulonglong * 3),
     ]
+
+
+class PeerBuf(C.Structure):
+    """struct sfr_peer_buf: one symmetric buffer as this rank sees it"""
+    _fields_ = [("ptrs", C.c_void_p * MAX_PEERS), ("multicast", C.c_void_p)]
+
+
+class PeerGeom(C.Structure):
+    """struct sfr_peer_geom"""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("lo", C.c_int64), ("n_local", C.c_int64)]
 
 
 SELECT_STATE_BYTES = C.sizeof(SelectState)
@@ -122,6 +136,19 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.sfr_select_threshold_value.argtypes = [vp, vp, vp]
     lib.sfr_soft_threshold.restype = C.c_int
     lib.sfr_soft_threshold.argtypes = [vp, vp, i64, vp, vp]
+    lib.sfr_peer_pad_bytes.restype = i64
+    lib.sfr_peer_pad_bytes.argtypes = []
+    lib.sfr_peer_barrier.restype = C.c_int
+    lib.sfr_peer_barrier.argtypes = [C.POINTER(PeerBuf), C.c_int, C.c_int, vp, vp, C.c_int, C.c_uint64, vp]
+    lib.sfr_peer_reduce.restype = C.c_int
+    lib.sfr_peer_reduce.argtypes = [C.POINTER(PeerBuf), C.c_int, C.POINTER(PeerGeom), C.c_int, C.c_int, vp, vp, vp,
+                                    vp, f32, vp]
+    lib.sfr_peer_fused_update.restype = C.c_int
+    lib.sfr_peer_fused_update.argtypes = [vp, vp, C.POINTER(PeerBuf), C.c_int, C.c_int, C.c_int, vp, vp, vp, vp,
+                                          C.POINTER(PeerBuf), C.POINTER(PeerBuf), C.c_int, C.POINTER(PeerGeom),
+                                          C.POINTER(UpdateArgs), vp, vp, vp, vp]
+    lib.sfr_peer_broadcast.restype = C.c_int
+    lib.sfr_peer_broadcast.argtypes = [vp, C.POINTER(PeerBuf), C.c_int, C.POINTER(PeerGeom), C.c_int, vp]
     if lib.sfr_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libsfron_b200 ABI {lib.sfr_abi_version()} != binding {ABI_VERSION}")
     if path == LIB_PATH:
@@ -134,7 +161,20 @@ def _check(code: int, where: str) -> None:
         raise SfrError(code, where, load().sfr_error_string(code).decode())
 
 
+# Devices of the tensors handed to `_ptr` since the last launch.  Every wrapper evaluates its `_ptr(...)` arguments
+# left to right and `_stream()` last, so `_stream()` sees exactly the tensors of its own call: it insists that they
+# share ONE device and returns that device's current stream.  The library (DeviceScope, csrc/api.cu) launches on
+# the device that owns the buffers, so a `HotPath(device="cuda:1")` works whatever the current device is.
+_seen_devices: list = []
+
+
 def _stream() -> int:
+    devs = set(_seen_devices)
+    _seen_devices.clear()
+    if len(devs) > 1:
+        raise SfrError(ERR_ARG, "launch", f"tensors of one call live on different devices: {sorted(map(str, devs))}")
+    if devs:
+        return torch.cuda.current_stream(devs.pop()).cuda_stream
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -147,6 +187,7 @@ def _ptr(t: Optional[torch.Tensor], dtype=None, what: str = "tensor") -> Optiona
         raise SfrError(ERR_ARG, what, "expected a contiguous tensor")
     if dtype is not None and t.dtype not in (dtype if isinstance(dtype, tuple) else (dtype,)):
         raise SfrError(ERR_ARG, what, f"expected dtype {dtype}, got {t.dtype}")
+    _seen_devices.append(t.device)
     return t.data_ptr()
 
 
@@ -176,9 +217,10 @@ def fisher_accum(acc: torch.Tensor, g: torch.Tensor, divisor: float, *,
         rows, stride = g.shape[0], g.stride(0)
         if g.shape[1] != n or g.stride(1) != 1:
             raise SfrError(ERR_ARG, "fisher_accum", "g must be [rows, n] with unit inner stride")
-        gptr = g.data_ptr()
         if not g.is_cuda:
             raise SfrError(ERR_NO_DEVICE, "fisher_accum", "expected a CUDA tensor")
+        gptr = g.data_ptr()
+        _seen_devices.append(g.device)
     else:
         if g.numel() != n:
             raise SfrError(ERR_ARG, "fisher_accum", f"g has {g.numel()} elements, acc has {n}")
@@ -333,3 +375,89 @@ def soft_threshold(p: torch.Tensor, p0: torch.Tensor, threshold: torch.Tensor) -
         raise SfrError(ERR_ARG, "soft_threshold", "size mismatch")
     _check(load().sfr_soft_threshold(_ptr(p, torch.float32, "p"), _ptr(p0, torch.float32, "p0"), p.numel(),
                                      _ptr(threshold, torch.float32, "threshold"), _stream()), "sfr_soft_threshold")
+
+
+# ---- cross-GPU exchange fused with the kernels (csrc/peer.cu) -----------------------------------------
+def peer_buf(ptrs: Sequence[int], multicast: int = 0) -> PeerBuf:
+    """struct sfr_peer_buf from the mapped device addresses of one symmetric buffer (ptrs[r] = rank r's copy)."""
+    if not 1 <= len(ptrs) <= MAX_PEERS:
+        raise SfrError(ERR_ARG, "peer_buf", f"1..{MAX_PEERS} ranks supported, got {len(ptrs)}")
+    b = PeerBuf()
+    for r, p in enumerate(ptrs):
+        b.ptrs[r] = int(p)
+    b.multicast = int(multicast) or None
+    return b
+
+
+def peer_buf_offset(b: PeerBuf, world: int, byte_offset: int) -> PeerBuf:
+    """The same symmetric buffer seen from `byte_offset` (a multiple of 16) onwards."""
+    out = PeerBuf()
+    for r in range(world):
+        out.ptrs[r] = b.ptrs[r] + byte_offset
+    out.multicast = (b.multicast + byte_offset) if b.multicast else None
+    return out
+
+
+def peer_pad_bytes() -> int:
+    return int(load().sfr_peer_pad_bytes())
+
+
+def peer_barrier(pad: PeerBuf, world: int, rank: int, vals: Optional[torch.Tensor] = None,
+                 sums: Optional[torch.Tensor] = None, timeout_ns: int = 0) -> None:
+    """Cross-GPU barrier on the current stream; `vals` (device float64[k<=8]) are summed over ranks, in rank
+    order, into `sums` on every rank."""
+    nvals = 0 if vals is None else vals.numel()
+    if nvals and (sums is None or sums.numel() < nvals):
+        raise SfrError(ERR_ARG, "peer_barrier", "sums must hold as many doubles as vals")
+    _check(load().sfr_peer_barrier(C.byref(pad), world, rank, _ptr(vals, torch.float64, "vals"),
+                                   _ptr(sums, torch.float64, "sums"), nvals, int(timeout_ns), _stream()),
+           "sfr_peer_barrier")
+
+
+def peer_reduce(g: PeerBuf, g_dtype: torch.dtype, geom: PeerGeom, transport: int, average: bool, *,
+                g_red: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+                sumsq: Optional[torch.Tensor] = None, fisher: Optional[torch.Tensor] = None,
+                fisher_divisor: float = 1.0) -> None:
+    for name, t in (("g_red", g_red), ("mask", mask), ("fisher", fisher)):
+        if t is not None and t.numel() != geom.n_local:
+            raise SfrError(ERR_ARG, "peer_reduce", f"{name} has {t.numel()} elements, the shard has {geom.n_local}")
+    gd = F32 if g_dtype == torch.float32 else BF16 if g_dtype == torch.bfloat16 else None
+    if gd is None:
+        raise SfrError(ERR_ARG, "peer_reduce", f"gradient dtype {g_dtype} not supported (fp32 | bf16)")
+    _check(load().sfr_peer_reduce(C.byref(g), gd, C.byref(geom), transport, int(bool(average)),
+                                  _ptr(g_red, torch.float32, "g_red"), _ptr(mask, _MASK_DTYPES, "mask"),
+                                  _ptr(sumsq, torch.float64, "sumsq"), _ptr(fisher, torch.float32, "fisher"),
+                                  float(fisher_divisor), _stream()), "sfr_peer_reduce")
+
+
+def peer_fused_update(p: torch.Tensor, geom: PeerGeom, args: UpdateArgs, *, g_red: Optional[torch.Tensor] = None,
+                      g: Optional[PeerBuf] = None, g_dtype: torch.dtype = torch.float32, g_transport: int = XP_P2P,
+                      average: bool = True, m: Optional[torch.Tensor] = None, v: Optional[torch.Tensor] = None,
+                      mask: Optional[torch.Tensor] = None, ema: Optional[torch.Tensor] = None,
+                      bc_f32: Optional[PeerBuf] = None, bc_bf16: Optional[PeerBuf] = None,
+                      bc_transport: int = XP_P2P, clip_sumsq: Optional[torch.Tensor] = None,
+                      step_counter: Optional[torch.Tensor] = None,
+                      consts_scratch: Optional[torch.Tensor] = None) -> None:
+    n = geom.n_local
+    for name, t in (("p", p), ("g_red", g_red), ("m", m), ("v", v), ("mask", mask), ("ema", ema)):
+        if t is not None and t.numel() != n:
+            raise SfrError(ERR_ARG, "peer_fused_update", f"{name} has {t.numel()} elements, the shard has {n}")
+    if (g is None) == (g_red is None):
+        raise SfrError(ERR_ARG, "peer_fused_update", "exactly one gradient source: g_red (local) or g (peers)")
+    gd = F32 if g_dtype == torch.float32 else BF16
+    args.g_dtype = gd
+    _check(load().sfr_peer_fused_update(
+        _ptr(p, torch.float32, "p"), _ptr(g_red, torch.float32, "g_red"), C.byref(g) if g is not None else None, gd,
+        g_transport, int(bool(average)), _ptr(m, torch.float32, "m"), _ptr(v, torch.float32, "v"),
+        _ptr(mask, _MASK_DTYPES, "mask"), _ptr(ema, torch.float32, "ema"),
+        C.byref(bc_f32) if bc_f32 is not None else None, C.byref(bc_bf16) if bc_bf16 is not None else None,
+        bc_transport, C.byref(geom), C.byref(args), _ptr(clip_sumsq, torch.float64, "clip_sumsq"),
+        _ptr(step_counter, torch.int64, "step_counter"), _ptr(consts_scratch, torch.uint8, "consts_scratch"),
+        _stream()), "sfr_peer_fused_update")
+
+
+def peer_broadcast(src: torch.Tensor, dst: PeerBuf, geom: PeerGeom, transport: int) -> None:
+    if src.numel() != geom.n_local or src.element_size() not in (2, 4):
+        raise SfrError(ERR_ARG, "peer_broadcast", "src must be this rank's shard of 2- or 4-byte elements")
+    _check(load().sfr_peer_broadcast(_ptr(src, what="src"), C.byref(dst), src.element_size(), C.byref(geom), transport,
+                                     _stream()), "sfr_peer_broadcast")

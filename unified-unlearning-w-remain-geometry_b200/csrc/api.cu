@@ -1,29 +1,80 @@
 // api.cu — library introspection, device geometry cache, and the flat-gradient gather.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace sfr {
 
-const DeviceGeometry& device_geometry() {
-  static DeviceGeometry geo = [] {
-    DeviceGeometry g;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) {
-      cudaGetLastError();
-      return g;
-    }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
-      cudaGetLastError();
-      return g;
-    }
-    g.sm_count = prop.multiProcessorCount;
-    g.cc_major = prop.major;
-    g.cc_minor = prop.minor;
-    // The kernels are compiled for sm_100a only: anything else cannot run them.
-    g.ok = (prop.major == 10);
+namespace {
+constexpr int kMaxDevices = 64;
+thread_local int tls_scope_device = -1;  // device entered by the innermost DeviceScope of this thread
+
+DeviceGeometry query_geometry(int dev) {
+  DeviceGeometry g;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    cudaGetLastError();
     return g;
-  }();
-  return geo;
+  }
+  g.sm_count = prop.multiProcessorCount;
+  g.cc_major = prop.major;
+  g.cc_minor = prop.minor;
+  // The kernels are compiled for sm_100a only: anything else cannot run them.
+  g.ok = (prop.major == 10);
+  return g;
+}
+
+const DeviceGeometry& geometry_of(int dev) {
+  static DeviceGeometry none;
+  if (dev < 0 || dev >= kMaxDevices) return none;
+  // one slot per ordinal, each initialised once (thread-safe: function-local statics in the lambdas)
+  static DeviceGeometry slots[kMaxDevices];
+  static std::once_flag flags[kMaxDevices];
+  std::call_once(flags[dev], [dev] { slots[dev] = query_geometry(dev); });
+  return slots[dev];
+}
+}  // namespace
+
+const DeviceGeometry& device_geometry() {
+  int dev = tls_scope_device;
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    dev = -1;
+  }
+  return geometry_of(dev);
+}
+
+DeviceScope::DeviceScope(const void* anchor) {
+  if (cudaGetDevice(&prev_) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  dev_ = prev_;
+  if (anchor != nullptr) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, anchor) == cudaSuccess) {
+      if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) dev_ = at.device;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  if (dev_ != prev_) {
+    if (cudaSetDevice(dev_) != cudaSuccess) {
+      cudaGetLastError();
+      dev_ = prev_;
+      return;
+    }
+    switched_ = true;
+  }
+  outer_ = tls_scope_device;
+  tls_scope_device = dev_;
+  entered_ = true;
+  ok_ = geometry_of(dev_).ok;
+}
+
+DeviceScope::~DeviceScope() {
+  if (entered_) tls_scope_device = outer_;
+  if (switched_) cudaSetDevice(prev_);
 }
 
 namespace {
@@ -92,7 +143,7 @@ extern "C" int sfr_gather_segments(float* flat, const void* const* srcs, const i
   SFR_REQUIRE_PTR(srcs);
   SFR_REQUIRE_PTR(offsets);
   SFR_REQUIRE_PTR(sizes);
-  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  SFR_ENTER_DEVICE(flat);
   const int64_t nchunks = (total + kGatherChunk - 1) / kGatherChunk;
   const int grid = persistent_grid(nchunks, 16);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -36,8 +36,30 @@ struct DeviceGeometry {
   bool ok = false;
 };
 
-// Cached per process (one GPU per process in this framework).
+// Geometry of the device the calling thread has entered (DeviceScope below), cached per device ordinal.
 const DeviceGeometry& device_geometry();
+
+// Every entry point runs on the device that OWNS its buffers, not on whatever device happens to be
+// current: the scope looks up the device of an anchor pointer, switches to it for the duration of the
+// call (launches, function attributes, geometry) and switches back.  One process per GPU is the normal
+// deployment, but a process that drives several GPUs (or has not called cudaSetDevice) gets the same results.
+class DeviceScope {
+ public:
+  explicit DeviceScope(const void* anchor);
+  ~DeviceScope();
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+  bool ok() const { return ok_; }
+  int device() const { return dev_; }
+
+ private:
+  int prev_ = -1;
+  int dev_ = -1;
+  int outer_ = -1;
+  bool switched_ = false;
+  bool entered_ = false;
+  bool ok_ = false;
+};
 
 // Persistent grid: enough CTAs to fill every SM `ctas_per_sm` times, but never more
 // than there are tiles.
@@ -195,6 +217,9 @@ __device__ __forceinline__ uint32_t select_key(float x) {
   do {                         \
     if ((p) != nullptr && !sfr::aligned16(p)) return SFR_ERR_ALIGN; \
   } while (0)
+#define SFR_ENTER_DEVICE(anchor)              \
+  sfr::DeviceScope device_scope__(anchor);    \
+  if (!device_scope__.ok()) return SFR_ERR_NO_DEVICE
 #define SFR_LAUNCH_STATUS()                \
   do {                                     \
     cudaError_t e__ = cudaGetLastError();  \

@@ -139,7 +139,7 @@ extern "C" int sfr_ewc_penalty(const float* p, const float* p_star, const float*
   SFR_REQUIRE_ALIGNED(p_star);
   SFR_REQUIRE_ALIGNED(fisher);
   SFR_REQUIRE_ALIGNED(g);
-  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  SFR_ENTER_DEVICE(p);
   const int64_t nvec = n >> 2;
   const int64_t tile = (int64_t)kThreads * kUnroll;
   const int grid = persistent_grid((nvec + tile - 1) / tile, 16 * 128);
@@ -151,7 +151,7 @@ extern "C" int sfr_select_threshold_value(const sfr_select_state* state, float* 
   using namespace sfr;
   SFR_REQUIRE_PTR(state);
   SFR_REQUIRE_PTR(out);
-  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  SFR_ENTER_DEVICE(state);
   select_threshold_value_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(state, out);
   SFR_LAUNCH_STATUS();
 }
@@ -166,7 +166,7 @@ extern "C" int sfr_soft_threshold(float* p, const float* p0, int64_t n, const fl
   SFR_REQUIRE_PTR(threshold_dev);
   SFR_REQUIRE_ALIGNED(p);
   SFR_REQUIRE_ALIGNED(p0);
-  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  SFR_ENTER_DEVICE(p);
   const int64_t nvec = n >> 2;
   const int grid = persistent_grid((nvec + kThreads - 1) / kThreads, 16 * 128);
   soft_threshold_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, p0, n, threshold_dev);

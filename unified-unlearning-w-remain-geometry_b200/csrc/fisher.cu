@@ -98,7 +98,7 @@ extern "C" int sfr_fisher_accum(float* acc, const void* g, int g_dtype, int64_t 
   if (g_dtype != SFR_F32 && g_dtype != SFR_BF16) return SFR_ERR_ARG;
   // every row must start 16-byte aligned: stride a multiple of 4 fp32 / 8 bf16 elements
   if (rows > 1 && (row_stride < n || (row_stride & (g_dtype == SFR_F32 ? 3 : 7)) != 0)) return SFR_ERR_ARG;
-  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  SFR_ENTER_DEVICE(acc);
 
   const int64_t nvec = n >> 2;
   const int64_t tile = (int64_t)kThreads * kUnroll;

@@ -135,7 +135,7 @@ extern "C" int sfr_ratio_mask_multi(const float* ff, const float* rf, int64_t n,
   SFR_REQUIRE_ALIGNED(rf);
   SFR_REQUIRE_ALIGNED(masks);
   if (n_thresholds > 1 && (mask_stride < n || (mask_stride & 15) != 0)) return SFR_ERR_ARG;
-  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  SFR_ENTER_DEVICE(ff);
   Thresholds th;
   for (int k = 0; k < SFR_MAX_THRESHOLDS; ++k)
     th.v[k] = k < n_thresholds ? thresholds_host[k] : 0.f;

@@ -19,6 +19,8 @@
 // Between hist and scan a multi-GPU caller all-reduces `bins` (<= 512 KB) over NCCL;
 // everything else is shard-local.  All steps are stream-ordered; the host never has to
 // read anything back.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace sfr {
@@ -771,7 +773,7 @@ extern "C" int sfr_select_init(sfr_select_state* state, unsigned long long* bins
   using namespace sfr;
   SFR_REQUIRE_PTR(state);
   SFR_REQUIRE_PTR(bins);
-  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  SFR_ENTER_DEVICE(state);
   select_init_kernel<<<(SFR_SELECT_BINS_ALLOC + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(state, bins, k);
   SFR_LAUNCH_STATUS();
 }
@@ -790,17 +792,19 @@ static int select_hist_impl(const float* a, const float* b, int key_mode, float 
   if (key_mode != SFR_KEY_ABS) SFR_REQUIRE_PTR(b);
   SFR_REQUIRE_ALIGNED(a);
   SFR_REQUIRE_ALIGNED(b);
-  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  SFR_ENTER_DEVICE(state);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t nvec = n >> 2;
   if (pass == 0) {
-    static bool attr_done = false;
+    // the opt-in to 128 KB of dynamic shared memory is per device (and this may be called from any thread)
+    static std::atomic<bool> attr_done_on[64];
     const int smem = SFR_SELECT_BINS0 * (int)sizeof(unsigned int);
-    if (!attr_done) {
+    std::atomic<bool>& attr_done = attr_done_on[device_scope__.device() & 63];
+    if (!attr_done.load(std::memory_order_acquire)) {
       cudaFuncSetAttribute(select_hist0_kernel<SFR_KEY_ABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       cudaFuncSetAttribute(select_hist0_kernel<SFR_KEY_RATIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       cudaFuncSetAttribute(select_hist0_kernel<SFR_KEY_ABSDIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      attr_done = true;
+      attr_done.store(true, std::memory_order_release);
     }
     const int64_t tile = (int64_t)kHistThreads * kHistUnroll;
     const int grid = persistent_grid((nvec + tile - 1) / tile, 1);
@@ -852,7 +856,7 @@ extern "C" int sfr_select_scan(int pass, sfr_select_state* state, unsigned long 
   if (pass != 0 && pass != 1) return SFR_ERR_ARG;
   SFR_REQUIRE_PTR(state);
   SFR_REQUIRE_PTR(bins);
-  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  SFR_ENTER_DEVICE(state);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int nbins = pass == 0 ? SFR_SELECT_BINS0 : SFR_SELECT_BINS1;
   select_scan_kernel<<<nbins / kScanCtaBins, kScanThreads, 0, s>>>(pass, state, bins);
@@ -884,7 +888,7 @@ extern "C" int sfr_select_apply(const float* a, const float* b, int key_mode, fl
   SFR_REQUIRE_ALIGNED(a);
   SFR_REQUIRE_ALIGNED(b);
   SFR_REQUIRE_ALIGNED(mask);
-  if (!device_geometry().ok) return SFR_ERR_NO_DEVICE;
+  SFR_ENTER_DEVICE(state);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t nchunks = (n + kChunk - 1) / kChunk;
   const int grid = persistent_grid(nchunks, 8);

@@ -220,6 +220,9 @@ class ShardedHotPath(HotPath):
     def __init__(self, shards: ShardGroup, device, opt: OptConfig, **kw):
         super().__init__(shards.n_local, device, opt, **kw)
         self.shards = shards
+        self._local_bins: Optional[torch.Tensor] = None
+        self.xchg: Optional["PeerExchange"] = None
+        self._g_red: dict = {}
 
     def reduce_scalar_(self, t: torch.Tensor) -> None:
         self.shards.all_reduce_(t)
@@ -231,7 +234,10 @@ class ShardedHotPath(HotPath):
         self.shards.all_reduce_(bins[:count])
 
     def keep_local_bins_(self, bins: torch.Tensor) -> Optional[torch.Tensor]:
-        return bins.clone()
+        if self._local_bins is None:                                  # persistent: no allocation per select
+            self._local_bins = torch.empty(capi.SELECT_BINS1, dtype=bins.dtype, device=bins.device)
+        self._local_bins.copy_(bins[:capi.SELECT_BINS1])
+        return self._local_bins
 
     def tie_base_(self, state: torch.Tensor, local_bins: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         """Number of threshold-equal keys on lower ranks, entirely on the device (no host read of the select
@@ -252,3 +258,215 @@ class ShardedHotPath(HotPath):
         masks = super().ratio_masks(thresholds, **kw)
         self.shards.all_reduce_(self.zero_count)
         return masks
+
+    # ---- data-parallel steps over NVLink peer memory (csrc/peer.cu) --------------------------------------
+    # The reference's DataParallel loops (DiT/forget.py:193,285-322; DiT/generate_fisher.py:173,216-291;
+    # DDPM/runners/diffusion.py:1060,1126-1180,1270-1281) reduce every GPU's gradient onto GPU 0, update
+    # there, and re-broadcast.  Here each rank pulls ITS shard of the summed gradient straight out of the
+    # peers' gradient buffers inside the kernel that consumes it, and pushes its updated weights into
+    # every rank's weight buffer from the kernel that produced them.
+    def attach_exchange(self, xchg: "PeerExchange") -> None:
+        if xchg.shards is not self.shards:
+            raise ValueError("the exchange and the hot path must share one ShardGroup")
+        self.xchg = xchg
+
+    def _need_xchg(self) -> "PeerExchange":
+        if self.xchg is None:
+            raise capi.SfrError(capi.ERR_ARG, "ShardedHotPath", "no PeerExchange attached (attach_exchange)")
+        return self.xchg
+
+    def reduced(self, slot: str) -> torch.Tensor:
+        """Local fp32 buffer for a reduced gradient shard (one per slot name, allocated once)."""
+        t = self._g_red.get(slot)
+        if t is None:
+            t = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+            self._g_red[slot] = t
+        return t
+
+    def dp_fisher_accumulate(self, which: str, g: "SymBuffer", divisor: float, *, average: bool = True,
+                             keep: Optional[str] = None, clip_max_norm: Optional[float] = None) -> None:
+        """K1 on the data-parallel mean gradient: barrier, then ONE kernel that pulls this shard of every
+        rank's `g`, averages and accumulates F += gbar**2 / divisor (keep="slot": the reduced shard is also left in
+        `self.reduced(slot)` for a following step on the same gradients).  With `clip_max_norm` (DDPM Fisher of
+        the clipped gradient) the norm has to be global first: reduce + sum of squares, summed across ranks on
+        the barrier, then the shard-local clipped K1."""
+        x = self._need_xchg()
+        acc = self.buffer({"forget": "forget_fisher", "remain": "remain_fisher"}.get(which, which))
+        x.barrier()
+        if clip_max_norm is None:
+            capi.peer_reduce(g.buf, g.tensor.dtype, x.geom, x.reduce_transport, average, fisher=acc, fisher_divisor=divisor,
+                             g_red=self.reduced(keep) if keep else None)
+            self._t("fisher_accum")
+            x.barrier()
+            return
+        red = self.reduced(keep or "_clip")
+        self.sumsq.zero_()
+        capi.peer_reduce(g.buf, g.tensor.dtype, x.geom, x.reduce_transport, average, g_red=red, sumsq=self.sumsq)
+        x.barrier(self.sumsq, self.sumsq)
+        capi.fisher_accum(acc, red, divisor, clip_sumsq=self.sumsq, clip_max_norm=clip_max_norm)
+        self._t("fisher_accum_clipped")
+
+    def dp_step(self, p: torch.Tensor, g, *, weights: Optional["SymBuffer"] = None,
+                weights_bf16: Optional["SymBuffer"] = None, mask: Optional[torch.Tensor] = None,
+                mask_order: str = "mask_then_clip", max_norm: Optional[float] = None, ema: bool = False,
+                lr: Optional[float] = None, average: bool = True, keep: str = "_step") -> None:
+        """One optimizer step of the sharded data-parallel loop.
+
+        p: this rank's fp32 weight shard (a view of `weights.tensor[lo:hi]`, or the fp32 master shard in bf16 mode).
+        g: a SymBuffer holding every rank's FULL gradient (reduced inside the kernels), or a local fp32
+           tensor with this rank's already reduced shard (e.g. `self.reduced(slot)` left by dp_fisher_accumulate).
+        weights / weights_bf16: full-vector symmetric buffers that receive the updated shard on EVERY rank.
+        No clip: barrier -> reduce + K3 + push in one kernel -> barrier.
+        Clip:    barrier -> reduce + masked sum of squares -> barrier carrying the norm -> K3 + push -> barrier."""
+        x = self._need_xchg()
+        from_peers = isinstance(g, SymBuffer)
+        flags = 0
+        if mask is not None:
+            flags |= capi.F_MASK if mask_order == "mask_then_clip" else capi.F_MASK_AFTER_CLIP
+        sgd = self.opt.kind == "sgd"
+        if self.step_dev is None and sgd and self.opt.momentum != 0.0 and not self.has("m"):
+            flags |= capi.F_SGD_FIRST_STEP
+        clip = None
+        g_red = None if from_peers else g
+        if from_peers:
+            x.barrier()                                   # every rank's backward has written its gradient
+        if max_norm is not None:
+            norm_mask = mask if (mask is not None and mask_order == "mask_then_clip") else None
+            self.sumsq.zero_()
+            if from_peers:
+                g_red = self.reduced(keep)
+                capi.peer_reduce(g.buf, g.tensor.dtype, x.geom, x.reduce_transport, average, g_red=g_red, mask=norm_mask,
+                                 sumsq=self.sumsq)
+            else:
+                capi.masked_sumsq(g_red, norm_mask, self.sumsq)
+            self._t("masked_sumsq")
+            x.barrier(self.sumsq, self.sumsq)             # the clip norm's all-reduce rides on the barrier
+            clip = self.sumsq
+        self.step_count += 1
+        a = self._args(flags, ema, max_norm, lr)
+        use_ema = ema and self.ema_mode != "none"
+        capi.peer_fused_update(
+            p, x.geom, a, g_red=g_red, g=g.buf if g_red is None else None,
+            g_dtype=g.tensor.dtype if g_red is None else torch.float32, g_transport=x.reduce_transport, average=average,
+            m=None if (sgd and self.opt.momentum == 0.0) else self.m, v=None if sgd else self.v, mask=mask,
+            ema=self.slow if use_ema else None, bc_f32=None if weights is None else weights.buf,
+            bc_bf16=None if weights_bf16 is None else weights_bf16.buf, bc_transport=x.push_transport, clip_sumsq=clip,
+            step_counter=self.step_dev,
+            consts_scratch=self._consts_dev if (clip is not None or self.step_dev is not None) else None)
+        self._t("fused_update_ema" if use_ema else "fused_update")
+        x.barrier()                                       # gradients may be overwritten; every weight store has landed
+
+    def dp_forget_step(self, p, g, *, mask: Optional[torch.Tensor] = None, use_mask: bool = True, **kw) -> None:
+        """grad *= mask ; clip ; step on the data-parallel mean gradient (DiT/forget.py:285-299 under DataParallel)."""
+        if mask is None and use_mask:
+            mask = self.require_mask()
+        self.dp_step(p, g, mask=mask if use_mask else None, ema=False, **kw)
+
+    def dp_remain_step(self, p, g, *, ema: bool = True, **kw) -> None:
+        """[clip ;] step ; EMA on the data-parallel mean gradient (DiT/forget.py:310-322 under DataParallel)."""
+        self.dp_step(p, g, mask=None, ema=ema, **kw)
+
+
+class SymBuffer:
+    """One symmetric buffer: the local tensor plus the addresses every rank's copy has in THIS process."""
+
+    def __init__(self, tensor: torch.Tensor, buf: "capi.PeerBuf", handle, world: int):
+        self.tensor, self.buf, self.handle, self.world = tensor, buf, handle, world
+
+    @property
+    def has_multicast(self) -> bool:
+        return bool(self.buf.multicast)
+
+
+class PeerExchange:
+    """NVLink peer-memory plumbing of the data-parallel hot path (one process per GPU).
+
+    Torch's symmetric-memory allocator provides what a C caller would get from cuMem* / cuMulticast*: buffers
+    that every rank of the group maps (`buffer_ptrs`) and, on an NVSwitch fabric, one multicast address per
+    buffer.  Nothing else of torch is on the data path: reduction, update, broadcast and the barrier are the
+    library's kernels (csrc/peer.cu).
+
+    transport: "auto", "p2p", "multimem", or "<reduce>+<push>" (e.g. "p2p+multimem") to choose separately how
+    gradients are pulled and how weights are pushed.
+    """
+
+    def __init__(self, shards: ShardGroup, device, transport: str = "auto", timeout_s: float = 30.0):
+        if shards.world > capi.MAX_PEERS:
+            raise capi.SfrError(capi.ERR_ARG, "PeerExchange", f"at most {capi.MAX_PEERS} ranks (one NVSwitch box)")
+        if shards.n_local and shards.lo % 16:
+            raise capi.SfrError(capi.ERR_ALIGN, "PeerExchange", "shard starts must be multiples of 16 elements")
+        self.shards = shards
+        self.device = torch.device(device)
+        self.group = shards.group if shards.group is not None else dist.group.WORLD
+        self.timeout_ns = int(timeout_s * 1e9)
+        self._want = transport
+        # what "auto" means when the fabric has multicast (measured, tools/xchg_bench.py -> profiles/r2_xchg_*.jsonl)
+        self._auto = (capi.XP_P2P, capi.XP_P2P) if shards.world <= 2 else (capi.XP_MULTIMEM, capi.XP_MULTIMEM)
+        self._buffers: List[SymBuffer] = []
+        self.geom = capi.PeerGeom(shards.world, shards.rank, shards.lo, shards.n_local)
+        self.pad = self.alloc(capi.peer_pad_bytes() // 8, torch.int64)         # zero-filled by alloc()
+        self._vals = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self.barriers = 0
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=shards.group)                   # every rank's pad is zero before the first epoch
+
+    # transport = "<reduce>" or "<reduce>+<push>" with each of auto | p2p | multimem, e.g. "p2p+multimem":
+    # gradients pulled through the mapped pointers, weights pushed through the multicast address.
+    def _pick(self, which: int) -> int:
+        want = self._want.split("+")
+        want = want[which] if len(want) > 1 else want[0]
+        if want == "p2p":
+            return capi.XP_P2P
+        data = self._buffers[1:] or self._buffers
+        mc = all(b.has_multicast for b in data)
+        if want == "multimem":
+            if not mc:
+                raise capi.SfrError(capi.ERR_ARG, "PeerExchange", "multimem requested but a buffer has no multicast address")
+            return capi.XP_MULTIMEM
+        if want != "auto":
+            raise capi.SfrError(capi.ERR_ARG, "PeerExchange", f"unknown transport {want!r}")
+        if not mc:
+            return capi.XP_P2P
+        return self._auto[which]
+
+    @property
+    def reduce_transport(self) -> int:
+        return self._pick(0)
+
+    @property
+    def push_transport(self) -> int:
+        return self._pick(1)
+
+    @property
+    def transport_name(self) -> str:
+        names = {capi.XP_P2P: "p2p", capi.XP_MULTIMEM: "multimem"}
+        r, p = names[self.reduce_transport], names[self.push_transport]
+        return r if r == p else f"{r}+{p}"
+
+    def alloc(self, numel: int, dtype: torch.dtype) -> SymBuffer:
+        """Collective: every rank allocates the same buffer (zero-filled) and maps the others'."""
+        import torch.distributed._symmetric_memory as symm
+        t = symm.empty(int(numel), dtype=dtype, device=self.device)
+        h = symm.rendezvous(t, self.group)
+        t.zero_()
+        ptrs = [int(p) for p in h.buffer_ptrs]
+        if ptrs[self.shards.rank] != t.data_ptr():
+            raise capi.SfrError(capi.ERR_ARG, "PeerExchange.alloc", "symmetric buffer is not at the start of its allocation")
+        b = SymBuffer(t, capi.peer_buf(ptrs, int(getattr(h, "multicast_ptr", 0) or 0)), h, self.shards.world)
+        self._buffers.append(b)
+        return b
+
+    def barrier(self, vals: Optional[torch.Tensor] = None, sums: Optional[torch.Tensor] = None) -> None:
+        """Cross-GPU barrier on the current stream (a kernel, not a host wait).  `vals` (device float64, <= 8):
+        their sum over ranks, in rank order, is left in `sums` on every rank."""
+        capi.peer_barrier(self.pad.buf, self.shards.world, self.shards.rank, vals, sums, self.timeout_ns)
+        self.barriers += 1
+
+    def check(self) -> None:
+        """Raise if a barrier ever timed out on this rank (synchronises the device)."""
+        if int(self.pad.tensor[1].item()) != 0:
+            raise RuntimeError("sfr_peer_barrier timed out: a peer rank stopped participating")
+
+    def all_gather_(self, shard: torch.Tensor, full: SymBuffer) -> None:
+        """Push this rank's shard into every rank's copy of `full` (the all-gather alone), between two barriers."""
+        capi.peer_broadcast(shard, full.buf, self.geom, self.push_transport)

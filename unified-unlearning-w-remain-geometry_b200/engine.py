@@ -64,6 +64,10 @@ class HotPath:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.zero_count = torch.zeros(capi.MAX_THRESHOLDS, dtype=torch.int64, device=self.device)
         self._select = None
+        # a saliency mask exists only once it was BUILT (ratio_mask / topk_mask) or LOADED (set_buffer / load_mask):
+        # forget_step(use_mask=True) without one raises instead of multiplying every gradient by a zero buffer
+        # (the reference applies no mask at all when mask_path is unset: DDPM/runners/diffusion.py:1050)
+        self._mask_ready = False
         self.select_two_pass = True    # False: pass 1 without the provisional mask, apply streams the vector again
         # replay-safe mode (CUDA graphs): the optimizer step counter lives on the device
         self.step_dev: Optional[torch.Tensor] = None
@@ -107,6 +111,8 @@ class HotPath:
         if t.numel() != self.n or t.device != self.device:
             raise ValueError(f"buffer {role}: wrong size or device")
         self._buf[role] = t.contiguous()
+        if role == "mask":
+            self._mask_ready = True
 
     @property
     def forget_fisher(self) -> torch.Tensor:
@@ -131,6 +137,18 @@ class HotPath:
     @property
     def slow(self) -> torch.Tensor:
         return self.buffer("slow")
+
+    def mark_mask_ready(self) -> None:
+        """For callers that filled `self.mask` themselves."""
+        self._mask_ready = True
+
+    def require_mask(self) -> torch.Tensor:
+        if not self._mask_ready:
+            raise capi.SfrError(
+                capi.ERR_ARG, "HotPath", "use_mask=True but no saliency mask has been built (ratio_mask / topk_mask) "
+                "or loaded (set_buffer('mask', ...) / load_mask); pass use_mask=False for the reference's unmasked "
+                "run (mask_path unset)")
+        return self.mask
 
     def init_slow(self, p: torch.Tensor) -> None:
         """EMAHelper.register / `ema = deepcopy(model)` / `ori_model = deepcopy(model)`:
@@ -160,6 +178,8 @@ class HotPath:
         self.zero_count.zero_()
         capi.ratio_mask(self.forget_fisher, self.remain_fisher, threshold, mask, self.zero_count, eps)
         self._t("ratio_mask")
+        if out is None:
+            self._mask_ready = True
         return mask
 
     def ratio_masks(self, thresholds: Sequence[float], *, eps: float = 1e-15) -> torch.Tensor:
@@ -197,6 +217,8 @@ class HotPath:
         capi.select_scan(1, state, bins)
         tie_base = self.tie_base_(state, local_bins)
         capi.select_apply(values, other, mode, state, tie_base, scratch, mask, eps)
+        if out is None:
+            self._mask_ready = True
         return mask
 
     def kth_smallest_absdiff(self, a: torch.Tensor, b: torch.Tensor, k: int) -> torch.Tensor:
@@ -302,7 +324,7 @@ class HotPath:
         """grad *= mask ; clip_grad_norm_(max_norm) ; optimizer.step()
         (sfron.py:201-206; runners/diffusion.py:1126-1138; DiT/forget.py:289-299)."""
         if mask is None and use_mask:
-            mask = self.mask
+            mask = self.require_mask()
         self._step(p, g, mask=mask if use_mask else None, mask_order=mask_order, max_norm=max_norm,
                    ema=False, lr=lr, zero_grad=zero_grad, p_bf16=p_bf16)
 
@@ -321,7 +343,7 @@ class HotPath:
         """SalUn's single step on the joint forget+remain loss: clip_grad_norm_ ; grad *= mask ;
         optimizer.step() ; EMA (runners/diffusion.py:575-594 — the clip precedes the mask there)."""
         if mask is None and use_mask:
-            mask = self.mask
+            mask = self.require_mask()
         self._step(p, g, mask=mask if use_mask else None, mask_order=mask_order, max_norm=max_norm,
                    ema=ema, lr=lr, zero_grad=zero_grad, p_bf16=p_bf16)
 
@@ -350,18 +372,26 @@ class HostGradientFeeder:
     """
 
     def __init__(self, n: int, device, slots: Sequence[str] = ("forget", "remain"),
-                 dtype: torch.dtype = torch.float32, depth: int = 2):
+                 dtype: torch.dtype = torch.float32, depth: int = 2,
+                 buffers: Optional[Sequence[Dict[str, torch.Tensor]]] = None):
+        """dtype: fp32, or bf16 host gradients (half the PCIe bytes; the kernels widen them exactly).
+        buffers: `depth` dicts slot -> device tensor to copy into instead of allocating — e.g. views of
+        symmetric (peer-mapped) gradient buffers, so the data-parallel kernels read them in place."""
         self.device = torch.device(device)
         self.slots = tuple(slots)
-        self.depth = depth
+        self.depth = depth if buffers is None else len(buffers)
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        self.buffers = [{s: torch.empty(n, dtype=dtype, device=self.device) for s in self.slots}
-                        for _ in range(depth)]
-        self.ready = [torch.cuda.Event() for _ in range(depth)]
-        self.free = [torch.cuda.Event() for _ in range(depth)]
+        if buffers is None:
+            buffers = [{s: torch.empty(n, dtype=dtype, device=self.device) for s in self.slots}
+                       for _ in range(depth)]
+        self.buffers = [dict(b) for b in buffers]
+        self.ready = [torch.cuda.Event() for _ in range(self.depth)]
+        self.free = [torch.cuda.Event() for _ in range(self.depth)]
         self._submitted = 0
         self._acquired = 0
-        self.bytes_per_step = n * torch.empty(0, dtype=dtype).element_size() * len(self.slots)
+        self.current_index = -1
+        first = self.buffers[0][self.slots[0]]
+        self.bytes_per_step = n * first.element_size() * len(self.slots)
 
     def submit(self, **host_tensors: torch.Tensor) -> None:
         if self._submitted - self._acquired >= self.depth:
@@ -374,7 +404,8 @@ class HostGradientFeeder:
                 h = host_tensors[s]
                 if not h.is_pinned():
                     raise ValueError(f"{s}: host gradient buffers must be pinned for an asynchronous copy")
-                self.buffers[i][s].copy_(h, non_blocking=True)
+                dst = self.buffers[i][s]
+                dst[:h.numel()].copy_(h, non_blocking=True)      # (a padded device buffer keeps its tail)
             self.ready[i].record(self.copy_stream)
         self._submitted += 1
 
@@ -383,7 +414,7 @@ class HostGradientFeeder:
             raise RuntimeError("nothing submitted")
         i = self._acquired % self.depth
         torch.cuda.current_stream(self.device).wait_event(self.ready[i])
-        self._current = i
+        self._current = self.current_index = i
         self._acquired += 1
         return self.buffers[i]
 
