@@ -85,6 +85,13 @@ SFR_API int sfr_fisher_accum(float* acc, const void* g, int g_dtype, int64_t row
                      const double* clip_sumsq, float clip_max_norm,
                      sfr_stream_t stream);
 
+/* SalUn saliency accumulation (the input of the K2b top-k mask):  acc[i] <- acc[i] + g[i] * coef
+ * replaces  `clip_grad_norm_(...)` + `gradients[name] += param.grad.data.cpu()`
+ *   DDPM/runners/diffusion.py:985-994 (clipped), Classification/unlearn/salun.py:163-169 (unclipped)
+ * coef as in sfr_fisher_accum when clip_sumsq != NULL, else 1 (no multiply).  Bit-exact (mul, then add). */
+SFR_API int sfr_grad_accum(float* acc, const void* g, int g_dtype, int64_t n,
+                   const double* clip_sumsq, float clip_max_norm, sfr_stream_t stream);
+
 /* ===========================================================================
  * K2a  ratio saliency mask
  *   mask[i] = ((ff[i] + eps) / (rf[i] + eps)) >= threshold ;  *zero_count += #(mask == 0)

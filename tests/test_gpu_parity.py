@@ -104,6 +104,30 @@ def test_k1_clipped_gradient_ddpm(sfr, dev):
         assert close(hp.forget_fisher, acc["w"])
 
 
+@pytest.mark.parametrize("n", [5, 4099, 1_000_003])
+def test_saliency_accumulate_matches_clip_then_add(sfr, dev, n):
+    """SalUn mask input: `clip_grad_norm_ ; gradients[name] += grad` (runners/diffusion.py:985-994) in one fused
+    pass.  Unclipped (salun.py:163-169) it is bit-exact; clipped it follows the oracle's clip to 1e-6 (the clip
+    coefficient comes from a double-precision norm here, from torch's fp32 norm there)."""
+    hp = sfr.HotPath(n, dev, sfr.OptConfig())
+    acc_ref = torch.zeros(n)
+    g = gen(21)
+    for _ in range(3):
+        x = torch.randn(n, generator=g) * 0.3
+        acc_ref += x
+        hp.saliency_accumulate(x.to(dev))
+    assert bits_equal(hp.buffer("grad_sum").cpu(), acc_ref)
+    hp.buffer("grad_sum").zero_()
+    acc_ref = torch.zeros(n)
+    for scale in (5.0, 1e-4, 2.0):                      # norms above and below max_norm
+        x = torch.randn(n, generator=g) * scale
+        y = x.clone()
+        O.clip_grad_norm([y], 1.0)
+        acc_ref += y
+        hp.saliency_accumulate(x.to(dev), clip_max_norm=1.0)
+    assert close(hp.buffer("grad_sum"), acc_ref)
+
+
 def test_k1_bf16_gradients(sfr, dev):
     n = 33_333
     x = torch.randn(n, generator=gen(4)).bfloat16()

@@ -1,0 +1,204 @@
+"""Parity at BASELINE's REAL sizes and layouts (configs 1 and 2), kernels vs the per-tensor CPU oracle:
+
+  config 1  ResNet-18, 62 tensors, N1 = 11,173,962   SGD(m .9, wd 5e-4) + cosine LR + slow/fast   sfron.py:167-222,255-259
+  config 2  DDPM U-Net, 334 tensors, N2 = 38,632,323 Adam + clip 1.0 on both steps + EMA(1e-4)    runners/diffusion.py:1126-1180
+
+K1 / K2a / K2b bit-exact (K2b against the STABLE double argsort over all 38.6 M values, ties included), K3 within
+1e-6 over 10 iterations (20 optimizer steps).  Besides the pass/fail bar the test records the PURE relative error
+distribution of the updated weights (max and 99.99th percentile of |a-b|/|b| over elements with |b| > 1e-3 rms) in
+gpurun_out/r2_realsize_parity.jsonl, so the absolute floor of `close()` is a measured exception, not a blanket.
+The layouts come from the harness models (tools/), whose names / shapes / order are pinned to the reference's
+modules by tests/test_harness_models.py.
+"""
+import json
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT, bits_equal
+from oracle import sfron_oracle as O
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+pytestmark = pytest.mark.gpu
+OUT = os.path.join(ROOT, "gpurun_out", "r2_realsize_parity.jsonl")
+
+
+@pytest.fixture(scope="module")
+def sfr():
+    import sfron_b200
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    sfron_b200.capi.load()
+    return sfron_b200
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def named_shapes(which):
+    with torch.device("meta"):
+        if which == "resnet18":
+            from resnet18_cifar import ResNet18Harness
+            m = ResNet18Harness()
+        else:
+            from ddpm_unet import DDPMCondUNet
+            m = DDPMCondUNet()
+    shapes = [(n, tuple(p.shape)) for n, p in m.named_parameters() if p.requires_grad]
+    return shapes
+
+
+EXPECT = {"resnet18": (62, 11_173_962), "ddpm": (334, 38_632_323)}
+
+
+def split(flat, shapes):
+    out, off = {}, 0
+    for n, s in shapes:
+        k = math.prod(s)
+        out[n] = flat[off:off + k].view(s)
+        off += k
+    assert off == flat.numel()
+    return out
+
+
+def cat(d, shapes):
+    return torch.cat([d[n].reshape(-1) for n, _ in shapes])
+
+
+def close(a, b, rtol=1e-6):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    rms = b.pow(2).mean().sqrt().item()
+    return not bool(((a - b).abs() > rtol * (b.abs() + rms)).any())
+
+
+def rel_stats(a, b):
+    """Pure relative error over the elements that are not tiny: max and 99.99th percentile."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    rms = b.pow(2).mean().sqrt()
+    keep = b.abs() > 1e-3 * rms
+    r = ((a - b).abs() / b.abs())[keep]
+    r, _ = r.sort()
+    return {"elements": int(keep.sum()), "of": b.numel(), "max_rel": float(r[-1]),
+            "p9999_rel": float(r[min(r.numel() - 1, int(0.9999 * r.numel()))]),
+            "frac_above_1e-6": float((r > 1e-6).double().mean())}
+
+
+def record(**kw):
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    with open(OUT, "a") as f:
+        f.write(json.dumps(kw) + "\n")
+
+
+def gradients(n, gen, shapes, scale=0.05):
+    """Per-tensor scales differ by orders of magnitude, as real gradients do."""
+    g = torch.randn(n, generator=gen) * scale
+    off = 0
+    for i, (_, s) in enumerate(shapes):
+        k = math.prod(s)
+        g[off:off + k] *= 10.0 ** ((i % 5) - 2)
+        off += k
+    return g
+
+
+@pytest.mark.parametrize("which", ["resnet18", "ddpm"])
+def test_layout_is_the_reference_size(which):
+    shapes = named_shapes(which)
+    assert (len(shapes), sum(math.prod(s) for _, s in shapes)) == EXPECT[which]
+
+
+@pytest.mark.parametrize("which", ["resnet18", "ddpm"])
+def test_k1_k2a_bit_exact_at_real_size(sfr, dev, which):
+    shapes = named_shapes(which)
+    n = EXPECT[which][1]
+    gen = torch.Generator().manual_seed(11)
+    hp = sfr.HotPath(n, dev, sfr.OptConfig())
+    acc = {"forget": O.fisher_init([s[0] for s in shapes]), "remain": O.fisher_init([s[0] for s in shapes])}
+    batches = 3
+    for role in ("forget", "remain"):
+        for _ in range(batches):
+            g = gradients(n, gen, shapes)
+            O.fisher_accumulate(acc[role], split(g, shapes), batches)       # per named tensor, as the reference
+            hp.fisher_accumulate(role, g.to(dev), float(batches))
+    ff, rf = cat(acc["forget"], shapes), cat(acc["remain"], shapes)
+    assert bits_equal(hp.forget_fisher.cpu(), ff) and bits_equal(hp.remain_fisher.cpu(), rf)
+    for th in (0.5, 1.0, 3.0):
+        ref_mask, zeros, total = O.ratio_mask(acc["forget"], acc["remain"], th)
+        want = cat(ref_mask, shapes)
+        got = hp.ratio_mask(th)
+        assert torch.equal(got.cpu().bool(), want.bool()), f"ratio mask differs at th={th}"
+        assert int(hp.zero_count[0]) == zeros and total == n
+    record(test="k1_k2a", config=which, n=n, tensors=len(shapes), result="bit-exact")
+
+
+@pytest.mark.parametrize("which,ratio", [("resnet18", 0.2), ("ddpm", 0.5)])
+def test_k2b_stable_double_argsort_at_real_size(sfr, dev, which, ratio):
+    """salun.py:43 (ratio 0.2) / runners/diffusion.py:1003 (0.5): ranks = argsort(argsort(-|g|)) over ALL elements."""
+    shapes = named_shapes(which)
+    n = EXPECT[which][1]
+    gen = torch.Generator().manual_seed(12)
+    g = gradients(n, gen, shapes)
+    g[::7] = (g[::7] * 64).round() / 64                                   # ties, also at the threshold's magnitude
+    want = cat(O.topk_mask(split(g.abs(), shapes), ratio, stable=True), shapes)   # the reference accumulates |g|
+    hp = sfr.HotPath(n, dev, sfr.OptConfig())
+    got = hp.topk_mask(g.to(dev), int(n * ratio))
+    assert torch.equal(got.cpu().long(), want.long()), "top-k mask differs from the stable double argsort"
+    assert int(got.sum(dtype=torch.int64)) == int(n * ratio)
+    record(test="k2b", config=which, n=n, k=int(n * ratio), result="bit-exact vs stable argsort(argsort)")
+
+
+def test_k3_resnet18_sgd_cosine_slowfast_10_iterations(sfr, dev):
+    shapes = named_shapes("resnet18")
+    n = EXPECT["resnet18"][1]
+    gen = torch.Generator().manual_seed(13)
+    theta0 = torch.randn(n, generator=gen) * 0.05
+    mask = torch.rand(n, generator=gen) < 0.3
+    kw = dict(lr=0.01, momentum=0.9, weight_decay=5e-4)
+    ref = O.FlatReferenceLoop(dict(shapes), split(theta0, shapes), "sgd", kw, ema_mode="slowfast", ema_a=0.9)
+    hp = sfr.HotPath(n, dev, sfr.OptConfig(kind="sgd", **kw), ema_mode="slowfast", ema_a=0.9)
+    hp.set_buffer("mask", mask.to(dev).to(torch.uint8))
+    p = theta0.to(dev).clone()
+    hp.init_slow(p)
+    iters = 10
+    for it in range(iters):
+        lr = O.cosine_lr_scheduler(0.01, it, iters)                        # sfron.py:45-46,259
+        ref.set_lr(lr)
+        gf, gr = gradients(n, gen, shapes), gradients(n, gen, shapes)
+        ref.forget_step(split(gf, shapes), mask=split(mask, shapes), max_norm=7.0)     # sfron.py:201-206
+        ref.remain_step(split(gr, shapes), ema=True)                                    # sfron.py:213-222,255-257
+        hp.forget_step(p, gf.to(dev), max_norm=7.0, lr=lr)
+        hp.remain_step(p, gr.to(dev), lr=lr, ema=True)
+    want = ref.flat("p")
+    st = rel_stats(p, want)
+    record(test="k3", config="resnet18", n=n, tensors=len(shapes), optimizer_steps=2 * iters, **st)
+    assert close(p, want), st
+    assert close(hp.m, ref.flat("buf"))
+
+
+def test_k3_ddpm_adam_clip_ema_10_iterations(sfr, dev):
+    shapes = named_shapes("ddpm")
+    n = EXPECT["ddpm"][1]
+    gen = torch.Generator().manual_seed(14)
+    theta0 = torch.randn(n, generator=gen) * 0.05
+    mask = torch.rand(n, generator=gen) < 0.5
+    kw = dict(lr=2e-4, weight_decay=0.0, beta1=0.9, beta2=0.999, eps=1e-8)  # DDPM/functions/__init__.py:9-18
+    ref = O.FlatReferenceLoop(dict(shapes), split(theta0, shapes), "adam", kw, ema_mode="ddpm", ema_a=1e-4)
+    hp = sfr.HotPath(n, dev, sfr.OptConfig(kind="adam", lr=2e-4), ema_mode="ddpm", ema_a=1e-4)
+    hp.set_buffer("mask", mask.to(dev).to(torch.uint8))
+    p = theta0.to(dev).clone()
+    hp.init_slow(p)
+    iters = 10
+    for _ in range(iters):
+        gf, gr = gradients(n, gen, shapes), gradients(n, gen, shapes)
+        ref.forget_step(split(gf, shapes), mask=split(mask, shapes), max_norm=1.0)     # runners/diffusion.py:1126-1138
+        ref.remain_step(split(gr, shapes), max_norm=1.0, ema=True)                      # :1169-1180
+        hp.forget_step(p, gf.to(dev), max_norm=1.0)
+        hp.remain_step(p, gr.to(dev), max_norm=1.0, ema=True)
+    want = ref.flat("p")
+    st = rel_stats(p, want)
+    record(test="k3", config="ddpm", n=n, tensors=len(shapes), optimizer_steps=2 * iters, **st)
+    assert close(p, want), st
+    assert close(hp.slow, ref.flat("slow")) and close(hp.m, ref.flat("m")) and close(hp.v, ref.flat("v"))

@@ -112,8 +112,34 @@ def run_ours(args, dev, ac, rank, world):
         model = model.to(torch.bfloat16)      # bf16 working weights + grads; fp32 master / state in the kernels
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     opt = sfr.OptConfig(kind="adamw", lr=1e-4, weight_decay=0.0)
-    flat = sfr.FlatParams(model, dev, pad_multiple=16 * world)
-    if world > 1:
+    peer = world > 1 and args.dp_exchange.startswith("peer")
+    xchg, sym = None, {}
+    if peer:
+        # gradients and the weights the model reads live in symmetric (peer-mapped) memory: the data-parallel
+        # kernels pull gradient shards out of every rank's buffer and push updated weights into every rank's
+        import torch.distributed as dist
+        from sfron_b200.dist import PeerExchange, ShardGroup, ShardedHotPath
+        n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
+        n_pad = -(-n_train // (16 * world)) * (16 * world)
+        sg = ShardGroup(n_train, padded_len=n_pad)
+        xchg = PeerExchange(sg, dev, transport=args.dp_exchange.partition(":")[2] or "auto")
+
+        def alloc(role, numel, dtype):
+            if role == "p" and args.dtype == "bf16":          # fp32 master: only this rank's shard is ever used
+                return torch.zeros(numel, dtype=dtype, device=dev)
+            sym[role] = xchg.alloc(numel, dtype)
+            return sym[role].tensor
+
+        flat = sfr.FlatParams(model, dev, pad_multiple=16 * world, alloc=alloc)
+        assert flat.n == n_train and flat.n_padded == n_pad
+        hp = ShardedHotPath(sg, dev, opt, ema_mode="dit", ema_a=0.9999)
+        hp.attach_exchange(xchg)
+        lo, hi = sg.lo, sg.hi
+    else:
+        flat = sfr.FlatParams(model, dev, pad_multiple=16 * world)
+    if peer:
+        pass
+    elif world > 1:
         import torch.distributed as dist
         from sfron_b200.dist import ShardGroup, ShardedHotPath
         sg = ShardGroup(flat.n, padded_len=flat.n_padded)
@@ -156,9 +182,19 @@ def run_ours(args, dev, ac, rank, world):
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     ac = ac.to(dt)
 
-    def forget_iter(i):
-        x, t, noise, y_f, y_r = make_batch(args.batch_size, dev, gen, dtype=dt)
+    def forget_body(x, t, noise, y_f, y_r):
         (args.forget_alpha * -synthetic_loss(model, x, t, y_f, noise, ac)).backward()
+        if peer:
+            # barrier -> reduce + masked norm (one kernel over NVLink) -> barrier carrying the norm -> K3 + weight
+            # push (one kernel) -> barrier
+            hp.dp_forget_step(p_loc, sym["g"], weights=sym.get("p"), weights_bf16=sym.get("p_work"), max_norm=1.0)
+            flat.g.zero_()
+            synthetic_loss(model, x, t, y_r, noise, ac).backward()
+            # barrier -> reduce + K3 + EMA + weight push in ONE kernel -> barrier
+            hp.dp_remain_step(p_loc, sym["g"], weights=sym.get("p"), weights_bf16=sym.get("p_work"), ema=True)
+            hp.ema_only(flat.frozen, frozen_slow)
+            flat.g.zero_()
+            return
         # single GPU: the update kernel zeroes g on its way out (fused optimizer.zero_grad());
         # sharded: each rank only rewrites its slice, so the full local gradient is memset
         hp.forget_step(p_loc, grads(), max_norm=1.0, zero_grad=sg is None, p_bf16=w_loc)
@@ -172,6 +208,9 @@ def run_ours(args, dev, ac, rank, world):
             sg.all_gather_params_(weights_full)
             flat.g.zero_()
 
+    def forget_iter(i):
+        forget_body(*make_batch(args.batch_size, dev, gen, dtype=dt))
+
     flat.g.zero_()
     if args.cuda_graph:
         # Whole iteration (2 forward/backward passes in PyTorch + the hot-path kernels) captured ONCE and
@@ -181,18 +220,7 @@ def run_ours(args, dev, ac, rank, world):
         static = list(make_batch(args.batch_size, dev, gen, dtype=dt))
 
         def body():
-            x, t, noise, y_f, y_r = static
-            (args.forget_alpha * -synthetic_loss(model, x, t, y_f, noise, ac)).backward()
-            hp.forget_step(p_loc, grads(), max_norm=1.0, zero_grad=sg is None, p_bf16=w_loc)
-            if sg is not None:
-                sg.all_gather_params_(weights_full)
-                flat.g.zero_()
-            synthetic_loss(model, x, t, y_r, noise, ac).backward()
-            hp.remain_step(p_loc, grads(), ema=True, zero_grad=sg is None, p_bf16=w_loc)
-            hp.ema_only(flat.frozen, frozen_slow)
-            if sg is not None:
-                sg.all_gather_params_(weights_full)
-                flat.g.zero_()
+            forget_body(*static)
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -214,11 +242,17 @@ def run_ours(args, dev, ac, rank, world):
     else:
         res["forget_s_per_it"] = timed(forget_iter, args.steps, args.warmup, sync)
 
+    def fisher_step():
+        if peer:
+            hp.dp_fisher_accumulate("forget", sym["g"], 2000.0)     # barrier -> reduce + K1 in one kernel -> barrier
+        else:
+            hp.fisher_accumulate("forget", grads(), 2000.0)
+        flat.g.zero_()
+
     def fisher_iter(i):
         x, t, noise, y_f, _ = make_batch(args.batch_size, dev, gen, dtype=dt)
         synthetic_loss(model, x, t, y_f, noise, ac).backward()
-        hp.fisher_accumulate("forget", grads(), 2000.0)
-        flat.g.zero_()
+        fisher_step()
 
     if args.cuda_graph:
         static_f = list(make_batch(args.batch_size, dev, gen, dtype=dt))
@@ -226,8 +260,7 @@ def run_ours(args, dev, ac, rank, world):
         def fisher_body():
             x, t, noise, y_f, _ = static_f
             synthetic_loss(model, x, t, y_f, noise, ac).backward()
-            hp.fisher_accumulate("forget", grads(), 2000.0)
-            flat.g.zero_()
+            fisher_step()
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -247,6 +280,10 @@ def run_ours(args, dev, ac, rank, world):
         res["fisher_s_per_it"] = timed(fisher_graph_iter, args.steps, args.warmup, sync)
     else:
         res["fisher_s_per_it"] = timed(fisher_iter, args.steps, args.warmup, sync)
+    if xchg is not None:
+        torch.cuda.synchronize()
+        xchg.check()
+        res["transport"] = xchg.transport_name
     return res
 
 
@@ -262,9 +299,11 @@ def main():
                     help="ours arm only: bf16 working weights / gradients with fp32 master + state (BASELINE config 3)")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="ours arm: capture the whole forget iteration (collectives included) in a CUDA graph and replay it")
-    ap.add_argument("--dp-exchange", default="reduce_scatter", choices=["reduce_scatter", "allreduce", "bucketed"],
-                    help="bucketed: all-reduce in buckets started from autograd hooks while backward still runs "
-                         "(sfron_b200.dist.BucketedGradReducer; correctness covered by the gloo test, not yet timed on GPUs)")
+    ap.add_argument("--dp-exchange", default="peer",
+                    help="peer[:transport] (default): the library's fused exchange kernels over NVLink peer memory "
+                         "(transport auto | p2p | multimem | <reduce>+<push>); reduce_scatter | allreduce: NCCL collectives "
+                         "around the shard-local kernels; bucketed: NCCL all-reduce in buckets started from autograd "
+                         "hooks while backward still runs (sfron_b200.dist.BucketedGradReducer)")
     ap.add_argument("--bucket-mb", type=int, default=64)
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
@@ -290,7 +329,9 @@ def main():
     if args.arm in ("both", "ours"):
         r = run_ours(args, dev, ac, rank, world)
         out["ours" + ("_bf16" if args.dtype == "bf16" else "") + ("_cudagraph" if args.cuda_graph else "")] = {"forget_steps_per_s": 1 / r["forget_s_per_it"], "fisher_steps_per_s": 1 / r["fisher_s_per_it"],
-                       "global_batch": args.batch_size * world}
+                       "global_batch": args.batch_size * world,
+                       "dp_exchange": (args.dp_exchange if world > 1 else None),
+                       "transport": r.get("transport")}
     if rank == 0:
         line = json.dumps(out)
         print(line, flush=True)

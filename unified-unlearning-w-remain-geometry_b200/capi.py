@@ -33,7 +33,7 @@ EMA_NONE, EMA_DDPM, EMA_DIT, EMA_SLOWFAST = 0, 1, 2, 3
 F_MASK, F_MASK_AFTER_CLIP, F_ZERO_GRAD, F_SGD_FIRST_STEP, F_WRITE_BF16 = 1, 2, 4, 8, 16
 
 EXPORTED_SYMBOLS = (
-    "sfr_abi_version", "sfr_error_string", "sfr_device_info", "sfr_fisher_accum",
+    "sfr_abi_version", "sfr_error_string", "sfr_device_info", "sfr_fisher_accum", "sfr_grad_accum",
     "sfr_ratio_mask", "sfr_ratio_mask_multi", "sfr_select_init", "sfr_select_hist", "sfr_select_hist1_mask",
     "sfr_select_scan", "sfr_select_scratch_elems", "sfr_select_apply", "sfr_masked_sumsq",
     "sfr_fused_update", "sfr_ema_update", "sfr_gather_segments",
@@ -106,6 +106,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.sfr_device_info.argtypes = [C.POINTER(C.c_int)] * 3
     lib.sfr_fisher_accum.restype = C.c_int
     lib.sfr_fisher_accum.argtypes = [vp, vp, C.c_int, i64, i64, i64, f32, vp, f32, vp]
+    lib.sfr_grad_accum.restype = C.c_int
+    lib.sfr_grad_accum.argtypes = [vp, vp, C.c_int, i64, vp, f32, vp]
     lib.sfr_ratio_mask.restype = C.c_int
     lib.sfr_ratio_mask.argtypes = [vp, vp, i64, f32, f32, vp, vp, vp]
     lib.sfr_ratio_mask_multi.restype = C.c_int
@@ -228,6 +230,16 @@ def fisher_accum(acc: torch.Tensor, g: torch.Tensor, divisor: float, *,
     _check(load().sfr_fisher_accum(_ptr(acc, torch.float32, "acc"), gptr, _gdtype(g), rows, stride, n,
                                    float(divisor), _ptr(clip_sumsq, torch.float64, "clip_sumsq"),
                                    float(clip_max_norm), _stream()), "sfr_fisher_accum")
+
+
+def grad_accum(acc: torch.Tensor, g: torch.Tensor, *, clip_sumsq: Optional[torch.Tensor] = None,
+               clip_max_norm: float = 0.0) -> None:
+    """acc += g [* clip coefficient]: SalUn's accumulation of (clipped) batch gradients, one pass."""
+    if g.numel() != acc.numel():
+        raise SfrError(ERR_ARG, "grad_accum", f"g has {g.numel()} elements, acc has {acc.numel()}")
+    _check(load().sfr_grad_accum(_ptr(acc, torch.float32, "acc"), _ptr(g, what="g"), _gdtype(g), acc.numel(),
+                                 _ptr(clip_sumsq, torch.float64, "clip_sumsq"), float(clip_max_norm), _stream()),
+           "sfr_grad_accum")
 
 
 # ---- K2a -----------------------------------------------------------------------------------

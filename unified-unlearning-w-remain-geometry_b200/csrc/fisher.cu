@@ -21,13 +21,17 @@ constexpr int kCtasPerSm = 12;  // register cap 42; 16 resident when the variant
 constexpr int kUnroll = 2;      // independent 128-bit loads in flight per stream per thread
 constexpr int kGridWaves = 32;  // grid = SMs x 16 x 32 CTAs (tuned: tools/tune/tune_stream.cu)
 
-template <bool CLIP>
+// SQUARE: the Fisher term (g*coef)**2 / L.  !SQUARE: the gradient itself, for SalUn's saliency accumulation
+// `gradients[name] += param.grad` after clip_grad_norm_ (DDPM/runners/diffusion.py:985-994;
+// Classification/unlearn/salun.py:163-169, unclipped): two roundings, mul then add, as on the CPU.
+template <bool CLIP, bool SQUARE>
 __device__ __forceinline__ float fisher_term(float g, float coef, float divisor) {
   if constexpr (CLIP) g = __fmul_rn(g, coef);  // clip_grad_norm_: grad.mul_(coef)
+  if constexpr (!SQUARE) return g;
   return __fdiv_rn(__fmul_rn(g, g), divisor);  // g**2 / L   (true division, as on CPU)
 }
 
-template <int GT, bool CLIP>
+template <int GT, bool CLIP, bool SQUARE = true>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 fisher_accum_kernel(float* __restrict__ acc, const void* __restrict__ g, int64_t rows,
                     int64_t row_stride, int64_t n, float divisor,
@@ -57,10 +61,10 @@ fisher_accum_kernel(float* __restrict__ acc, const void* __restrict__ g, int64_t
       }
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        a[u].x = __fadd_rn(a[u].x, fisher_term<CLIP>(gg[u].x, coef, divisor));
-        a[u].y = __fadd_rn(a[u].y, fisher_term<CLIP>(gg[u].y, coef, divisor));
-        a[u].z = __fadd_rn(a[u].z, fisher_term<CLIP>(gg[u].z, coef, divisor));
-        a[u].w = __fadd_rn(a[u].w, fisher_term<CLIP>(gg[u].w, coef, divisor));
+        a[u].x = __fadd_rn(a[u].x, fisher_term<CLIP, SQUARE>(gg[u].x, coef, divisor));
+        a[u].y = __fadd_rn(a[u].y, fisher_term<CLIP, SQUARE>(gg[u].y, coef, divisor));
+        a[u].z = __fadd_rn(a[u].z, fisher_term<CLIP, SQUARE>(gg[u].z, coef, divisor));
+        a[u].w = __fadd_rn(a[u].w, fisher_term<CLIP, SQUARE>(gg[u].w, coef, divisor));
       }
     }
 #pragma unroll
@@ -76,7 +80,7 @@ fisher_accum_kernel(float* __restrict__ acc, const void* __restrict__ g, int64_t
     const int64_t i = tail0 + threadIdx.x;
     float a = acc[i];
     for (int64_t r = 0; r < rows; ++r)
-      a = __fadd_rn(a, fisher_term<CLIP>(load_g1<GT>(g, r * row_stride + i), coef, divisor));
+      a = __fadd_rn(a, fisher_term<CLIP, SQUARE>(load_g1<GT>(g, r * row_stride + i), coef, divisor));
     acc[i] = a;
   }
 }
@@ -114,5 +118,33 @@ extern "C" int sfr_fisher_accum(float* acc, const void* g, int g_dtype, int64_t 
     if (clip) SFR_K1(SFR_BF16, true); else SFR_K1(SFR_BF16, false);
   }
 #undef SFR_K1
+  SFR_LAUNCH_STATUS();
+}
+
+
+// SalUn saliency accumulation: acc += g [* clip coefficient]   (12 B/elem, one pass, no temporary)
+extern "C" int sfr_grad_accum(float* acc, const void* g, int g_dtype, int64_t n,
+                              const double* clip_sumsq, float clip_max_norm, sfr_stream_t stream) {
+  using namespace sfr;
+  if (n < 0) return SFR_ERR_ARG;
+  if (n == 0) return SFR_OK;
+  SFR_REQUIRE_PTR(acc);
+  SFR_REQUIRE_PTR(g);
+  SFR_REQUIRE_ALIGNED(acc);
+  SFR_REQUIRE_ALIGNED(g);
+  if (g_dtype != SFR_F32 && g_dtype != SFR_BF16) return SFR_ERR_ARG;
+  SFR_ENTER_DEVICE(acc);
+  const int64_t nvec = n >> 2;
+  const int64_t tile = (int64_t)kThreads * kUnroll;
+  const int grid = persistent_grid((nvec + tile - 1) / tile, 16 * kGridWaves);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define SFR_ACC(GT, CL) \
+  fisher_accum_kernel<GT, CL, false><<<grid, kThreads, 0, s>>>(acc, g, 1, n, n, 1.0f, clip_sumsq, clip_max_norm)
+  if (g_dtype == SFR_F32) {
+    if (clip_sumsq) SFR_ACC(SFR_F32, true); else SFR_ACC(SFR_F32, false);
+  } else {
+    if (clip_sumsq) SFR_ACC(SFR_BF16, true); else SFR_ACC(SFR_BF16, false);
+  }
+#undef SFR_ACC
   SFR_LAUNCH_STATUS();
 }

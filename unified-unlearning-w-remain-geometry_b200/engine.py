@@ -171,6 +171,22 @@ class HotPath:
             capi.fisher_accum(acc, g, divisor, clip_sumsq=self.sumsq, clip_max_norm=clip_max_norm)
             self._t("fisher_accum_clipped")
 
+    def saliency_accumulate(self, g: torch.Tensor, *, clip_max_norm: Optional[float] = None,
+                            role: str = "grad_sum") -> torch.Tensor:
+        """`clip_grad_norm_ ; gradients[name] += param.grad` of the SalUn mask generation
+        (DDPM/runners/diffusion.py:985-994; salun.py:163-169 without the clip): one norm pass + ONE
+        accumulate pass (12 B/elem), no temporary."""
+        acc = self.buffer(role)
+        if clip_max_norm is None:
+            capi.grad_accum(acc, g)
+        else:
+            self.sumsq.zero_()
+            capi.masked_sumsq(g, None, self.sumsq)
+            self.reduce_scalar_(self.sumsq)
+            capi.grad_accum(acc, g, clip_sumsq=self.sumsq, clip_max_norm=clip_max_norm)
+        self._t("saliency_accum")
+        return acc
+
     # ---- K2a --------------------------------------------------------------------------------------
     def ratio_mask(self, threshold: float, *, eps: float = 1e-15, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Writes the bool mask (uint8 storage) and leaves the zero count in `self.zero_count[0]`."""

@@ -131,10 +131,15 @@ class FlatParams:
     pad_multiple: allocate the flat buffers with a length rounded up to this many elements (the views
     and every kernel still cover exactly n elements) so that equal-sized shards exist for
     reduce-scatter / all-gather; the tail [n, n_padded) is never part of the logical vector.
+
+    alloc: optional `alloc(role, numel, dtype) -> zero-filled device tensor` for the buffers other ranks must
+    reach — role "g" (gradients), "p" (fp32 weights) and "p_work" (bf16 working weights) — e.g. the tensors of
+    `dist.PeerExchange.alloc`, so that the data-parallel kernels read / write them in place over NVLink.
     """
 
     def __init__(self, model: torch.nn.Module, device=None, *, grads_as_views: bool = True,
-                 grad_dtype: Optional[torch.dtype] = None, pad_multiple: int = 1):
+                 grad_dtype: Optional[torch.dtype] = None, pad_multiple: int = 1,
+                 alloc=None):
         named = list(model.named_parameters())
         train = [(n, p) for n, p in named if p.requires_grad]
         frozen = [(n, p) for n, p in named if not p.requires_grad]
@@ -157,11 +162,17 @@ class FlatParams:
         n = self.layout.numel
         self.n = n
         self.n_padded = (n + pad_multiple - 1) // pad_multiple * pad_multiple
-        self.p_padded = torch.zeros(self.n_padded, dtype=torch.float32, device=self.device)
-        self.g_padded = torch.zeros(self.n_padded, dtype=grad_dtype, device=self.device)
+        if alloc is None:
+            def alloc(_role, numel, dtype):
+                return torch.zeros(numel, dtype=dtype, device=self.device)
+        self.p_padded = alloc("p", self.n_padded, torch.float32)
+        self.g_padded = alloc("g", self.n_padded, grad_dtype)
+        for t_ in (self.p_padded, self.g_padded):
+            if t_.numel() != self.n_padded or t_.device != self.device:
+                raise ValueError("alloc() must return a tensor of the requested length on the model's device")
         self.p = self.p_padded[:n]
         self.g = self.g_padded[:n]
-        self.p_work_padded = (torch.zeros(self.n_padded, dtype=torch.bfloat16, device=self.device)
+        self.p_work_padded = (alloc("p_work", self.n_padded, torch.bfloat16)
                               if self.param_dtype == torch.bfloat16 else None)
         self.p_work = None if self.p_work_padded is None else self.p_work_padded[:n]
         weights = self.p if self.p_work is None else self.p_work        # what the module sees
@@ -206,25 +217,36 @@ class FlatParams:
         if self.grads_as_views:
             return self.g
         from . import capi
-        srcs, sizes, dt = [], [], None
+        srcs, keep, dt = [], [], None
         for seg, prm in zip(self.layout, self._train_params):
             if prm.grad is None:
                 raise RuntimeError(f"parameter {seg.name} has no gradient")
             gt = prm.grad
             if not gt.is_contiguous():
                 gt = gt.contiguous()
+                keep.append(gt)          # the temporary must outlive the gather launch (its block could be reused)
             dt = gt.dtype if dt is None else dt
             if gt.dtype != dt:
                 raise RuntimeError("mixed gradient dtypes")
             srcs.append(gt.data_ptr())
-            sizes.append(seg.numel)
         if self._gather_tables is None:
             offs = torch.tensor([s.offset for s in self.layout], dtype=torch.int64)
-            self._gather_tables = (offs.to(self.device), torch.tensor(sizes, dtype=torch.int64).to(self.device))
+            sizes = torch.tensor([s.numel for s in self.layout], dtype=torch.int64)
+            self._gather_tables = (offs.to(self.device), sizes.to(self.device))
+            self._gather_srcs_host = None
+            self._gather_srcs_dev = torch.empty(len(srcs), dtype=torch.int64, device=self.device)
         offs_d, sizes_d = self._gather_tables
-        srcs_d = torch.tensor(srcs, dtype=torch.int64).to(self.device, non_blocking=False)
-        capi.gather_segments(self.g, srcs_d, offs_d, sizes_d,
+        if srcs != self._gather_srcs_host:
+            # the pointer table is persistent: autograd usually hands back the same gradient storage step after
+            # step, so it is re-uploaded only when an address changed
+            self._gather_srcs_dev.copy_(torch.tensor(srcs, dtype=torch.int64))
+            self._gather_srcs_host = list(srcs)
+        capi.gather_segments(self.g, self._gather_srcs_dev, offs_d, sizes_d,
                              capi.F32 if dt == torch.float32 else capi.BF16, self.n)
+        if keep:
+            # stream-ordered: the caching allocator only reuses these blocks for work queued after the gather
+            for tmp in keep:
+                tmp.record_stream(torch.cuda.current_stream(self.device))
         return self.g
 
     def named_views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:

@@ -180,14 +180,8 @@ class DiffusionUnlearner:
         for i in range(n_batches):
             mhp.zero_grad()
             loss_fn(i).backward()
-            g = mhp.grads()
-            if self.cfg.clip_fisher is not None:      # clip_grad_norm_ before accumulating (:985-990)
-                mhp.hp.sumsq.zero_()
-                capi.masked_sumsq(g, None, mhp.hp.sumsq)
-                coef = torch.clamp(self.cfg.clip_fisher / (mhp.hp.sumsq.sqrt().float() + 1e-6), max=1.0)
-                acc += g.mul(coef)                   # grad.mul_(coef) ; gradients[name] += grad
-            else:
-                acc += g
+            # clip_grad_norm_ ; gradients[name] += grad  (:985-994) — norm pass + one fused accumulate pass
+            mhp.hp.saliency_accumulate(mhp.grads(), clip_max_norm=self.cfg.clip_fisher)
         mhp.zero_grad()
         k = int(mhp.layout.numel * ratio)
         mask = mhp.hp.topk_mask(acc, k)
