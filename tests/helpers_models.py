@@ -38,6 +38,29 @@ class TinyCond(nn.Module):
         self.conv_out = nn.Conv2d(6, 3, 3, padding=1)
 
 
+class TinyCondNet(TinyCond):
+    """TinyCond with the call interface of the reference's Conditional_Model (`model(x, t, c, mode="train"|"test",
+    cond_drop_prob=, cond_scale=)`, classifier-free guidance through `null_classes_emb`), so that the runner-level
+    drop-in (sfron_b200.methods.ddpm.Diffusion) can be driven end to end on synthetic data."""
+
+    def __init__(self, config=None):
+        super().__init__()
+
+    def _eps(self, x, t, c, drop):
+        cemb = self.classes_emb(c)
+        if drop > 0:
+            keep = torch.rand(x.shape[0], device=x.device) < (1 - drop)
+            cemb = torch.where(keep[:, None], cemb, self.null_classes_emb[None].expand_as(cemb))
+        h = self.conv_in(x) + (cemb + self.temb(t[:, None] / 1000.0))[:, :, None, None]
+        return self.conv_out(torch.tanh(h))
+
+    def forward(self, x, t, c, mode="train", cond_drop_prob=None, cond_scale=None):
+        if mode == "train":
+            return self._eps(x, t, c, 0.1 if cond_drop_prob is None else cond_drop_prob)
+        eps = self._eps(x, t, c, 0.0)
+        return eps if not cond_scale else (1 + cond_scale) * eps - cond_scale * self._eps(x, t, c, 1.0)
+
+
 class TinyLatentUNet(nn.Module):
     """Parameter structure of the 586-parameter stand-in U-Net make_golden.py's `sd_scripts` part put behind
     `model.model.diffusion_model` (keys are U-Net-local, as in the SD Fisher / mask files)."""
