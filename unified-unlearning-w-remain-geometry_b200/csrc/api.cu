@@ -50,7 +50,16 @@ DeviceScope::DeviceScope(const void* anchor) {
     return;
   }
   dev_ = prev_;
-  if (anchor != nullptr) {
+  // one visible device: nothing to look up (and no driver query on the launch path at all)
+  static const int device_count = [] {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+      cudaGetLastError();
+      c = 0;
+    }
+    return c;
+  }();
+  if (anchor != nullptr && device_count > 1) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, anchor) == cudaSuccess) {
       if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) dev_ = at.device;

@@ -138,8 +138,9 @@ __device__ __forceinline__ float ld_peer1(const void* base, int64_t i) {
 template <int GT>
 __device__ __forceinline__ float4 p2p_sum4(const GradSrc& s, int64_t gvec) {
   float4 v[kMaxPeers];
+  v[0] = ld_peer4<GT>(s.ptrs.p[0], gvec);  // world >= 1
 #pragma unroll
-  for (int r = 0; r < kMaxPeers; ++r)
+  for (int r = 1; r < kMaxPeers; ++r)
     if (r < s.world) v[r] = ld_peer4<GT>(s.ptrs.p[r], gvec);
   float4 a = v[0];
 #pragma unroll
@@ -156,7 +157,7 @@ __device__ __forceinline__ float4 p2p_sum4(const GradSrc& s, int64_t gvec) {
 // Four reduced (and averaged) gradients: elements 4*vec.. of the shard = 4*(lo_vec+vec).. of the vector.
 template <int GT, int GS>
 __device__ __forceinline__ float4 reduced_g4(const GradSrc& s, int64_t lo_vec, int64_t vec) {
-  float4 a;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   if constexpr (GS == GS_LOCAL) {
     return *(reinterpret_cast<const float4*>(s.local) + vec);
   } else if constexpr (GS == GS_P2P) {

@@ -21,10 +21,14 @@
 // read anything back.
 #include <atomic>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace sfr {
 namespace {
+
+namespace cg = cooperative_groups;
 
 // ---- key source ------------------------------------------------------------------------
 template <int MODE>
@@ -449,10 +453,10 @@ __device__ __forceinline__ void load_chunk_keys(const float* __restrict__ a, con
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kApplyThreads, MODE != SFR_KEY_ABS ? 2 : 4)
-select_tie_count_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps,
-                        int64_t n, const sfr_select_state* __restrict__ state,
-                        unsigned long long* __restrict__ scratch) {
+__device__ __forceinline__ void
+tie_count_body(const float* __restrict__ a, const float* __restrict__ b, float eps,
+               int64_t n, const sfr_select_state* __restrict__ state,
+               unsigned long long* __restrict__ scratch) {
   if (!ties_need_order(state)) return;
   const int64_t nchunks = (n + kChunk - 1) / kChunk;
   if (scratch[2 * nchunks] == 0ull) return;  // candidates did not overflow: counted from the list
@@ -476,9 +480,9 @@ select_tie_count_kernel(const float* __restrict__ a, const float* __restrict__ b
 // one CTA; only entries whose low key bits equal the threshold's touch a (zeroed) chunk counter.
 // When pass 1 left a provisional mask, the same walk also FINISHES the mask for the candidates: low bits
 // above the threshold's -> 1; equal -> 1 if every tie is selected, else left 0 for the ordered kernel.
-__global__ void __launch_bounds__(256, 8)
-select_resolve_candidates_kernel(int64_t n, const sfr_select_state* __restrict__ state,
-                                 unsigned long long* __restrict__ scratch, uint8_t* __restrict__ mask) {
+__device__ __forceinline__ void
+resolve_candidates_body(int64_t n, const sfr_select_state* __restrict__ state,
+                        unsigned long long* __restrict__ scratch, uint8_t* __restrict__ mask) {
   if (state->select_none || state->select_all) return;
   const int64_t nchunks = (n + kChunk - 1) / kChunk;
   unsigned long long* hdr = scratch + 2 * nchunks;
@@ -539,9 +543,9 @@ select_resolve_candidates_kernel(int64_t n, const sfr_select_state* __restrict__
 // contains a tie (a handful, except on degenerate inputs).
 constexpr int kScanBlock = 4096;  // chunks per scan block (= 33.5 M elements)
 
-__global__ void __launch_bounds__(256, 8)
-select_tie_block_sum_kernel(int64_t nchunks, const sfr_select_state* __restrict__ state,
-                            unsigned long long* __restrict__ scratch) {
+__device__ __forceinline__ void
+tie_block_sum_body(int64_t nchunks, const sfr_select_state* __restrict__ state,
+                   unsigned long long* __restrict__ scratch) {
   if (!ties_need_order(state)) return;
   __shared__ unsigned long long red[32];
   const int64_t nblocks = (nchunks + kScanBlock - 1) / kScanBlock;
@@ -556,10 +560,11 @@ select_tie_block_sum_kernel(int64_t nchunks, const sfr_select_state* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(1024, 1)
-select_tie_block_scan_kernel(int64_t nchunks, const sfr_select_state* __restrict__ state,
-                             const unsigned long long* __restrict__ tie_base,
-                             unsigned long long* __restrict__ scratch) {
+// (runs in ONE CTA of any size that is a multiple of 32 threads, up to 1024)
+__device__ __forceinline__ void
+tie_block_scan_body(int64_t nchunks, const sfr_select_state* __restrict__ state,
+                    const unsigned long long* __restrict__ tie_base,
+                    unsigned long long* __restrict__ scratch) {
   if (!ties_need_order(state)) return;
   __shared__ unsigned long long warp_tot[32];
   __shared__ unsigned long long carry_s;
@@ -567,7 +572,8 @@ select_tie_block_scan_kernel(int64_t nchunks, const sfr_select_state* __restrict
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long carry = tie_base ? *tie_base : 0ull;
   unsigned long long* sums = scratch + nchunks;
-  for (int64_t base = 0; base < nblocks; base += 1024) {
+  const int nwarps = (int)(blockDim.x >> 5);
+  for (int64_t base = 0; base < nblocks; base += blockDim.x) {
     const int64_t i = base + threadIdx.x;
     const unsigned long long mine = i < nblocks ? sums[i] : 0ull;
     unsigned long long incl = mine;
@@ -579,7 +585,7 @@ select_tie_block_scan_kernel(int64_t nchunks, const sfr_select_state* __restrict
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-      unsigned long long w = warp_tot[lane], wi = w;
+      unsigned long long w = lane < nwarps ? warp_tot[lane] : 0ull, wi = w;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const unsigned long long up = __shfl_up_sync(kFullMask, wi, o);
@@ -600,10 +606,10 @@ select_tie_block_scan_kernel(int64_t nchunks, const sfr_select_state* __restrict
 constexpr int kApplyUnroll = 4;
 
 template <int MODE>
-__global__ void __launch_bounds__(kApplyThreads, 4)
-select_apply_stream_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps,
-                           int64_t n, const sfr_select_state* __restrict__ state,
-                           const unsigned long long* __restrict__ scratch, uint8_t* __restrict__ mask) {
+__device__ __forceinline__ void
+apply_stream_body(const float* __restrict__ a, const float* __restrict__ b, float eps,
+                  int64_t n, const sfr_select_state* __restrict__ state,
+                  const unsigned long long* __restrict__ scratch, uint8_t* __restrict__ mask) {
   if (ties_need_order(state)) return;  // the ordered kernel below writes the mask instead
   const bool none = state->select_none != 0;
   const bool all = state->select_all != 0;
@@ -649,10 +655,10 @@ select_apply_stream_kernel(const float* __restrict__ a, const float* __restrict_
 
 // More threshold-equal keys than the budget: lowest flat index first.
 template <int MODE>
-__global__ void __launch_bounds__(kApplyThreads, MODE != SFR_KEY_ABS ? 2 : 4)
-select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps,
-                    int64_t n, const sfr_select_state* __restrict__ state,
-                    const unsigned long long* __restrict__ scratch, uint8_t* __restrict__ mask) {
+__device__ __forceinline__ void
+apply_ordered_body(const float* __restrict__ a, const float* __restrict__ b, float eps,
+                   int64_t n, const sfr_select_state* __restrict__ state,
+                   const unsigned long long* __restrict__ scratch, uint8_t* __restrict__ mask) {
   if (!ties_need_order(state)) return;  // the streaming kernel above wrote the mask
   __shared__ unsigned int warp_tot[kApplyThreads / 32];
   const uint32_t thr = state->thr_key;
@@ -752,6 +758,76 @@ select_apply_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
       }
     }
   }
+}
+
+
+// ---- the whole apply stage in ONE cooperative launch -------------------------------------------------
+// The stages above depend on each other grid-wide (tie counts -> block sums -> block bases -> ordered apply).
+// As separate launches (2 memsets + 6 kernels, most of them a few microseconds of work) they cost 74 us of
+// the 130 us select at the DDPM size (38.6 M elements) — launch latency, not bandwidth.  Here they are phases
+// of one persistent grid separated by grid-wide barriers; the branches on the device-side select state are
+// uniform over the grid, so every CTA reaches the same barriers.
+template <int MODE>
+__global__ void __launch_bounds__(kApplyThreads, MODE != SFR_KEY_ABS ? 2 : 3)
+select_apply_fused_kernel(const float* __restrict__ a, const float* __restrict__ b, float eps, int64_t n,
+                          const sfr_select_state* __restrict__ state,
+                          const unsigned long long* __restrict__ tie_base,
+                          unsigned long long* __restrict__ scratch, uint8_t* __restrict__ mask) {
+  cg::grid_group grid = cg::this_grid();
+  const int64_t nchunks = (n + kChunk - 1) / kChunk;
+  const bool order = ties_need_order(state);
+  if (order) {
+    // the per-chunk counters are accumulated into, and the tie-chunk list appended to: clear them first,
+    // so that apply may be repeated after one pass 1
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nchunks; i += (int64_t)gridDim.x * blockDim.x)
+      scratch[i] = 0ull;
+    if (blockIdx.x == 0 && threadIdx.x < 2) scratch[2 * nchunks + 5 + threadIdx.x] = 0ull;
+    grid.sync();
+  }
+  resolve_candidates_body(n, state, scratch, mask);   // list walk: finishes the provisional mask, counts ties
+  tie_count_body<MODE>(a, b, eps, n, state, scratch); // (only after a candidate overflow: streaming count)
+  if (order) {
+    grid.sync();
+    tie_block_sum_body(nchunks, state, scratch);
+    grid.sync();
+    if (blockIdx.x == 0) tie_block_scan_body(nchunks, state, tie_base, scratch);
+    grid.sync();
+    apply_ordered_body<MODE>(a, b, eps, n, state, scratch, mask);
+  } else {
+    apply_stream_body<MODE>(a, b, eps, n, state, scratch, mask);   // returns at once when the walk wrote the mask
+  }
+}
+
+// co-resident CTAs of the fused kernel, per device and key mode (occupancy x SMs)
+template <int MODE>
+int fused_grid(int device) {
+  static std::atomic<int> cached[64];
+  int g = cached[device & 63].load(std::memory_order_acquire);
+  if (g == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, select_apply_fused_kernel<MODE>, kApplyThreads, 0) !=
+            cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      per_sm = 1;
+    }
+    g = per_sm * device_geometry().sm_count;
+    cached[device & 63].store(g, std::memory_order_release);
+  }
+  return g;
+}
+
+template <int MODE>
+cudaError_t launch_apply_fused(int device, const float* a, const float* b, float eps, int64_t n,
+                               const sfr_select_state* state, const unsigned long long* tie_base,
+                               unsigned long long* scratch, uint8_t* mask, cudaStream_t s) {
+  const int64_t nchunks = (n + kChunk - 1) / kChunk;
+  int64_t want = nchunks > kMaxRegions * 4 ? nchunks : kMaxRegions * 4;
+  const int cap = fused_grid<MODE>(device);
+  const int grid = (int)(want < cap ? want : cap);
+  void* args[] = {(void*)&a, (void*)&b, (void*)&eps, (void*)&n, (void*)&state, (void*)&tie_base, (void*)&scratch,
+                  (void*)&mask};
+  return cudaLaunchCooperativeKernel((const void*)select_apply_fused_kernel<MODE>, dim3(grid), dim3(kApplyThreads),
+                                     args, 0, s);
 }
 
 __global__ void select_init_kernel(sfr_select_state* state, unsigned long long* bins,
@@ -890,26 +966,14 @@ extern "C" int sfr_select_apply(const float* a, const float* b, int key_mode, fl
   SFR_REQUIRE_ALIGNED(mask);
   SFR_ENTER_DEVICE(state);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int64_t nchunks = (n + kChunk - 1) / kChunk;
-  const int grid = persistent_grid(nchunks, 8);
-  const int sum_grid = persistent_grid((nchunks + kScanBlock - 1) / kScanBlock, 8);
-  const int64_t stile = (int64_t)kApplyThreads * kApplyUnroll;
-  const int sgrid = persistent_grid(((n >> 2) + stile - 1) / stile, 4);
-  // the per-chunk counters are accumulated into: clear them here so that apply is idempotent
-  cudaMemsetAsync(scratch, 0, (size_t)nchunks * sizeof(unsigned long long), s);
-  cudaMemsetAsync(scratch + 2 * nchunks + 5, 0, 2 * sizeof(unsigned long long), s);   // tie-chunk list: count, overflow
-  select_resolve_candidates_kernel<<<persistent_grid(kMaxRegions * 4, 8), 256, 0, s>>>(n, state, scratch, mask);
-#define SFR_APPLY(M)                                                                                     \
-  do {                                                                                                   \
-    select_tie_count_kernel<M><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch);             \
-    select_tie_block_sum_kernel<<<sum_grid, 256, 0, s>>>(nchunks, state, scratch);                       \
-    select_tie_block_scan_kernel<<<1, 1024, 0, s>>>(nchunks, state, tie_base, scratch);                  \
-    select_apply_kernel<M><<<grid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch, mask);           \
-    select_apply_stream_kernel<M><<<sgrid, kApplyThreads, 0, s>>>(a, b, eps, n, state, scratch, mask);   \
-  } while (0)
-  if (key_mode == SFR_KEY_ABS) SFR_APPLY(SFR_KEY_ABS);
-  else if (key_mode == SFR_KEY_RATIO) SFR_APPLY(SFR_KEY_RATIO);
-  else SFR_APPLY(SFR_KEY_ABSDIFF);
-#undef SFR_APPLY
+  cudaError_t e;
+  const int dev = device_scope__.device();
+  if (key_mode == SFR_KEY_ABS) e = launch_apply_fused<SFR_KEY_ABS>(dev, a, b, eps, n, state, tie_base, scratch, mask, s);
+  else if (key_mode == SFR_KEY_RATIO) e = launch_apply_fused<SFR_KEY_RATIO>(dev, a, b, eps, n, state, tie_base, scratch, mask, s);
+  else e = launch_apply_fused<SFR_KEY_ABSDIFF>(dev, a, b, eps, n, state, tie_base, scratch, mask, s);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return (int)e;
+  }
   SFR_LAUNCH_STATUS();
 }

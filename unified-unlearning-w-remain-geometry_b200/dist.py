@@ -221,6 +221,7 @@ class ShardedHotPath(HotPath):
         super().__init__(shards.n_local, device, opt, **kw)
         self.shards = shards
         self._local_bins: Optional[torch.Tensor] = None
+        self.select_graphs = False                 # the select's cross-rank reductions are torch.distributed calls
         self.xchg: Optional["PeerExchange"] = None
         self._g_red: dict = {}
 

@@ -64,6 +64,11 @@ class HotPath:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.zero_count = torch.zeros(capi.MAX_THRESHOLDS, dtype=torch.int64, device=self.device)
         self._select = None
+        # the whole select (every launch is stream-ordered, nothing is read back) replayed from one CUDA graph per
+        # (buffers, n, k): the first call runs eagerly, the second captures, later ones replay.  Off when the select
+        # spans ranks (its collectives are torch.distributed calls) — dist.ShardedHotPath clears the flag.
+        self.select_graphs = True
+        self._select_graph_cache: Dict[tuple, object] = {}
         # a saliency mask exists only once it was BUILT (ratio_mask / topk_mask) or LOADED (set_buffer / load_mask):
         # forget_step(use_mask=True) without one raises instead of multiplying every gradient by a zero buffer
         # (the reference applies no mask at all when mask_path is unset: DDPM/runners/diffusion.py:1050)
@@ -222,17 +227,40 @@ class HotPath:
         mode = capi.KEY_ABS if other is None else capi.KEY_RATIO
         state, bins, scratch = self._select_buffers()
         mask = self.mask if out is None else out
-        capi.select_init(state, bins, k)
-        capi.select_hist(values, other, mode, 0, state, bins, None, eps)
-        self.reduce_bins_(bins, capi.SELECT_BINS0)
-        capi.select_scan(0, state, bins)
-        # pass 1 also leaves the provisional mask, so apply only has to resolve the staged candidates
-        capi.select_hist(values, other, mode, 1, state, bins, scratch, eps, mask=mask if self.select_two_pass else None)
-        local_bins = self.keep_local_bins_(bins)
-        self.reduce_bins_(bins, capi.SELECT_BINS1)
-        capi.select_scan(1, state, bins)
-        tie_base = self.tie_base_(state, local_bins)
-        capi.select_apply(values, other, mode, state, tie_base, scratch, mask, eps)
+
+        def launches():
+            capi.select_init(state, bins, k)
+            capi.select_hist(values, other, mode, 0, state, bins, None, eps)
+            self.reduce_bins_(bins, capi.SELECT_BINS0)
+            capi.select_scan(0, state, bins)
+            # pass 1 also leaves the provisional mask, so apply only has to resolve the staged candidates
+            capi.select_hist(values, other, mode, 1, state, bins, scratch, eps,
+                             mask=mask if self.select_two_pass else None)
+            local_bins = self.keep_local_bins_(bins)
+            self.reduce_bins_(bins, capi.SELECT_BINS1)
+            capi.select_scan(1, state, bins)
+            tie_base = self.tie_base_(state, local_bins)
+            capi.select_apply(values, other, mode, state, tie_base, scratch, mask, eps)
+
+        if self.select_graphs and not torch.cuda.is_current_stream_capturing():
+            key = (values.data_ptr(), None if other is None else other.data_ptr(), mask.data_ptr(), values.numel(),
+                   int(k), mode, float(eps), self.select_two_pass)
+            entry = self._select_graph_cache.get(key)
+            if entry is None:
+                launches()
+                if len(self._select_graph_cache) >= 4:                      # a handful of live (buffers, k) pairs
+                    self._select_graph_cache.pop(next(iter(self._select_graph_cache)))
+                self._select_graph_cache[key] = "warm"
+            else:
+                if entry == "warm":
+                    with torch.cuda.device(self.device):
+                        entry = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(entry):
+                            launches()
+                    self._select_graph_cache[key] = entry
+                entry.replay()
+        else:
+            launches()
         if out is None:
             self._mask_ready = True
         return mask
