@@ -268,6 +268,17 @@ SFR_API int sfr_fused_update(float* p, void* g, float* m, float* v, const uint8_
                      long long* step_counter_dev, void* consts_scratch_dev,
                      sfr_stream_t stream);
 
+/* Clip norm + K3 in ONE cooperative launch, for small vectors (ResNet-18, an 8-way shard): zero *sumsq, accumulate
+ * sum((g*mask)^2) [mask only with SFR_F_MASK: the SalUn order clips the unmasked gradient], grid barrier, then the
+ * update of sfr_fused_update with coef = min(1, args->clip_max_norm / (sqrt(*sumsq) + 1e-6)).  Replaces four
+ * stream-ordered launches (memset, sfr_masked_sumsq, the scalar prep kernel, the update); the second read of g is
+ * served by the L2 when the vector fits.  *sumsq (device double) is left holding the norm's square, as after
+ * sfr_masked_sumsq.  step_counter_dev as in sfr_fused_update.  Same arithmetic, same results.  Single-GPU only: a
+ * sharded vector needs its norm summed across ranks between the two phases. */
+SFR_API int sfr_clipped_update(float* p, void* g, float* m, float* v, const uint8_t* mask,
+                     float* ema, void* p_bf16, int64_t n, const sfr_update_args* args,
+                     double* sumsq, long long* step_counter_dev, sfr_stream_t stream);
+
 /* EMA / slow-weight pass alone (frozen parameters that only the reference's EMA
  * loops touch, e.g. DiT pos_embed: DiT/forget.py:58-62). */
 SFR_API int sfr_ema_update(const float* p, float* ema, int64_t n, int ema_mode, double ema_a,

@@ -416,12 +416,17 @@ CASES = [
 @pytest.mark.parametrize("opt,kw,ema_mode,ema_a", CASES)
 @pytest.mark.parametrize("n", [1, 6, 4099, 200_001])
 @pytest.mark.parametrize("order", ["mask_then_clip", "clip_then_mask"])
-def test_k3_vs_torch_optim_trajectory(sfr, dev, opt, kw, ema_mode, ema_a, n, order):
+@pytest.mark.parametrize("launch", ["coop", "split"])
+def test_k3_vs_torch_optim_trajectory(sfr, dev, opt, kw, ema_mode, ema_a, n, order, launch):
+    """launch: clipped steps as ONE cooperative launch (sfr_clipped_update, the default for vectors of this size) or
+    as the separate norm / scalar-prep / update launches large vectors use — same arithmetic either way."""
     g = gen(n * 31 + len(opt))
     theta0 = torch.randn(n, generator=g) * 0.02
     mask = torch.rand(n, generator=g) < 0.35
     ref = flat_loop(n, theta0, opt, kw, ema_mode, ema_a)
     hp, p = engine_for(sfr, dev, n, theta0, opt, kw, ema_mode, ema_a)
+    if launch == "split":
+        hp.coop_max_elems = 0
     hp.set_buffer("mask", mask.to(torch.uint8).to(dev))
     for step in range(8):
         gf = torch.randn(n, generator=g) * (4.0 if step % 2 else 0.01)
@@ -550,7 +555,8 @@ def test_proximal_shrink_bit_exact(sfr, dev, n, frac):
 
 # =============================================================================== CUDA-graph replay
 @pytest.mark.parametrize("opt,kw,ema_mode,ema_a", [CASES[0], CASES[3], CASES[5]])
-def test_k3_cuda_graph_replay_advances_device_step(sfr, dev, opt, kw, ema_mode, ema_a):
+@pytest.mark.parametrize("launch", ["coop", "split"])
+def test_k3_cuda_graph_replay_advances_device_step(sfr, dev, opt, kw, ema_mode, ema_a, launch):
     """forget_step + remain_step captured once and replayed: the optimizer step (Adam bias corrections,
     SGD first-step buffer init) must advance on the device at every replay."""
     n = 50_003
@@ -560,6 +566,8 @@ def test_k3_cuda_graph_replay_advances_device_step(sfr, dev, opt, kw, ema_mode, 
     ref = flat_loop(n, theta0, opt, kw, ema_mode, ema_a)
     hp, p = engine_for(sfr, dev, n, theta0, opt, kw, ema_mode, ema_a)
     hp.set_buffer("mask", mask.to(torch.uint8).to(dev))
+    if launch == "split":
+        hp.coop_max_elems = 0
     hp.enable_graph_replay()
     gf_s, gr_s = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
 

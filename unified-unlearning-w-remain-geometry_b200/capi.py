@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = (
     "sfr_abi_version", "sfr_error_string", "sfr_device_info", "sfr_fisher_accum", "sfr_grad_accum",
     "sfr_ratio_mask", "sfr_ratio_mask_multi", "sfr_select_init", "sfr_select_hist", "sfr_select_hist1_mask",
     "sfr_select_scan", "sfr_select_scratch_elems", "sfr_select_apply", "sfr_masked_sumsq",
-    "sfr_fused_update", "sfr_ema_update", "sfr_gather_segments",
+    "sfr_fused_update", "sfr_clipped_update", "sfr_ema_update", "sfr_gather_segments",
     "sfr_ewc_penalty", "sfr_select_threshold_value", "sfr_soft_threshold",
     "sfr_peer_pad_bytes", "sfr_peer_barrier", "sfr_peer_reduce", "sfr_peer_fused_update", "sfr_peer_broadcast",
 )
@@ -128,6 +128,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.sfr_masked_sumsq.argtypes = [vp, C.c_int, vp, i64, vp, vp]
     lib.sfr_fused_update.restype = C.c_int
     lib.sfr_fused_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(UpdateArgs), vp, vp, vp, vp]
+    lib.sfr_clipped_update.restype = C.c_int
+    lib.sfr_clipped_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(UpdateArgs), vp, vp, vp]
     lib.sfr_ema_update.restype = C.c_int
     lib.sfr_ema_update.argtypes = [vp, vp, i64, C.c_int, f64, vp]
     lib.sfr_gather_segments.restype = C.c_int
@@ -348,6 +350,23 @@ def fused_update(p: torch.Tensor, g: torch.Tensor, m: Optional[torch.Tensor], v:
                                    _ptr(step_counter, torch.int64, "step_counter"),
                                    _ptr(consts_scratch, torch.uint8, "consts_scratch"), _stream()),
            "sfr_fused_update")
+
+
+def clipped_update(p: torch.Tensor, g: torch.Tensor, m: Optional[torch.Tensor], v: Optional[torch.Tensor],
+                   mask: Optional[torch.Tensor], ema: Optional[torch.Tensor], args: UpdateArgs, sumsq: torch.Tensor,
+                   p_bf16: Optional[torch.Tensor] = None, step_counter: Optional[torch.Tensor] = None) -> None:
+    """Clip norm + fused update in one cooperative launch (small vectors); leaves the squared norm in `sumsq`."""
+    n = p.numel()
+    for name, t in (("g", g), ("m", m), ("v", v), ("mask", mask), ("ema", ema), ("p_bf16", p_bf16)):
+        if t is not None and t.numel() != n:
+            raise SfrError(ERR_ARG, "clipped_update", f"{name} has {t.numel()} elements, p has {n}")
+    args.g_dtype = _gdtype(g)
+    _check(load().sfr_clipped_update(_ptr(p, torch.float32, "p"), _ptr(g, what="g"), _ptr(m, torch.float32, "m"),
+                                     _ptr(v, torch.float32, "v"), _ptr(mask, _MASK_DTYPES, "mask"),
+                                     _ptr(ema, torch.float32, "ema"), _ptr(p_bf16, torch.bfloat16, "p_bf16"), n,
+                                     C.byref(args), _ptr(sumsq, torch.float64, "sumsq"),
+                                     _ptr(step_counter, torch.int64, "step_counter"), _stream()),
+           "sfr_clipped_update")
 
 
 def ema_update(p: torch.Tensor, ema: torch.Tensor, ema_mode: int, ema_a: float) -> None:

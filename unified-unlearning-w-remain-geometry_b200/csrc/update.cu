@@ -18,10 +18,16 @@
 //   add(b, alpha)   -> fma(b, alpha, a)          lerp(w<.5) -> fma(end-start, w, start)
 //   addcmul(value)  -> fma(value*t1, t2, self)   addcdiv    -> self + (value*t1)/t2   (no fma)
 //   mul / div / sqrt / add with a Python scalar -> the scalar rounded to fp32 first.
+#include <atomic>
+
+#include <cooperative_groups.h>
+
 #include "update_core.cuh"
 
 namespace sfr {
 namespace {
+
+namespace cg = cooperative_groups;
 
 constexpr int kThreads = 256;
 
@@ -30,10 +36,11 @@ constexpr int kSumsqCtasPerSm = 8;
 constexpr int kSumsqUnroll = 4;
 constexpr int kSumsqGridWaves = 16;  // SMs x 8 x 16 CTAs, one double atomic each (tuned: tools/tune)
 
-template <int GT, bool MASK>
-__global__ void __launch_bounds__(kThreads, kSumsqCtasPerSm)
-masked_sumsq_kernel(const void* __restrict__ g, const uint8_t* __restrict__ mask, int64_t n,
-                    double* __restrict__ out) {
+// Sum over the grid of (g*mask)^2, accumulated into *out with one double atomic per CTA.  TPB = threads per CTA.
+template <int GT, bool MASK, int TPB>
+__device__ __forceinline__ void masked_sumsq_body(const void* __restrict__ g, const uint8_t* __restrict__ mask,
+                                                  int64_t n, double* __restrict__ out) {
+  constexpr int kThreads = TPB;
   __shared__ double scratch[32];
   const int64_t nvec = n >> 2;
   const int64_t tile = (int64_t)kThreads * kSumsqUnroll;
@@ -83,16 +90,23 @@ masked_sumsq_kernel(const void* __restrict__ g, const uint8_t* __restrict__ mask
   if (threadIdx.x == 0) atomicAdd(out, total);
 }
 
+template <int GT, bool MASK>
+__global__ void __launch_bounds__(kThreads, kSumsqCtasPerSm)
+masked_sumsq_kernel(const void* __restrict__ g, const uint8_t* __restrict__ mask, int64_t n,
+                    double* __restrict__ out) {
+  masked_sumsq_body<GT, MASK, kThreads>(g, mask, n, out);
+}
+
 constexpr int kUpdThreads = 128;  // small CTAs, one 128-vector tile per CTA (tuned: tools/tune/tune_stream.cu)
 constexpr int kUpdCtasPerSm = 6;
 
 template <int OPT, int EMA, int GT>
-__global__ void __launch_bounds__(kUpdThreads, kUpdCtasPerSm)
-fused_update_kernel(float* __restrict__ p, void* __restrict__ g, float* __restrict__ m,
-                    float* __restrict__ v, const uint8_t* __restrict__ mask,
-                    float* __restrict__ ema, void* __restrict__ p_bf16, int64_t n,
-                    UpdateConsts c_arg, const DevConsts* __restrict__ c_dev,
-                    const double* __restrict__ clip_sumsq) {
+__device__ __forceinline__ void
+fused_update_body(float* __restrict__ p, void* __restrict__ g, float* __restrict__ m,
+                  float* __restrict__ v, const uint8_t* __restrict__ mask,
+                  float* __restrict__ ema, void* __restrict__ p_bf16, int64_t n,
+                  const UpdateConsts& c_arg, const DevConsts* __restrict__ c_dev,
+                  const double* __restrict__ clip_sumsq) {
   UpdateConsts c = c_arg;
   float coef_dev = 1.0f;
   if (c_dev != nullptr) {
@@ -170,6 +184,46 @@ fused_update_kernel(float* __restrict__ p, void* __restrict__ g, float* __restri
   }
 }
 
+template <int OPT, int EMA, int GT>
+__global__ void __launch_bounds__(kUpdThreads, kUpdCtasPerSm)
+fused_update_kernel(float* __restrict__ p, void* __restrict__ g, float* __restrict__ m,
+                    float* __restrict__ v, const uint8_t* __restrict__ mask,
+                    float* __restrict__ ema, void* __restrict__ p_bf16, int64_t n,
+                    UpdateConsts c_arg, const DevConsts* __restrict__ c_dev,
+                    const double* __restrict__ clip_sumsq) {
+  fused_update_body<OPT, EMA, GT>(p, g, m, v, mask, ema, p_bf16, n, c_arg, c_dev, clip_sumsq);
+}
+
+// ---- clip norm + update in ONE cooperative launch (small vectors) ----------------------------------------
+// zero + masked sum of squares + step-dependent scalars + fused update are four launches of 2-10 us each when the
+// vector has ~1e7 elements (ResNet-18, an 8-way shard of DiT-XL/2): launch latency, not bandwidth.  As phases of one
+// persistent grid separated by two grid-wide barriers they cost one launch, and the second read of g hits the L2.
+template <int OPT, int EMA, int GT>
+__global__ void __launch_bounds__(kUpdThreads, kUpdCtasPerSm)
+clipped_update_coop_kernel(float* __restrict__ p, void* __restrict__ g, float* __restrict__ m,
+                           float* __restrict__ v, const uint8_t* __restrict__ mask,
+                           float* __restrict__ ema, void* __restrict__ p_bf16, int64_t n,
+                           sfr_update_args a, bool has_momentum, long long* step_counter,
+                           double* __restrict__ sumsq) {
+  cg::grid_group grid = cg::this_grid();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *sumsq = 0.0;
+    if (step_counter) ++(*step_counter);   // optimizer state['step'] lives on the device (CUDA-graph replay)
+  }
+  grid.sync();
+  // the norm clip_grad_norm_ sees: of the masked gradient (SFR-on order) or of the raw one (SalUn order / no mask)
+  if (a.flags & SFR_F_MASK) masked_sumsq_body<GT, true, kUpdThreads>(g, mask, n, sumsq);
+  else masked_sumsq_body<GT, false, kUpdThreads>(g, mask, n, sumsq);
+  grid.sync();
+  const long long step = step_counter ? *step_counter : (long long)a.step;
+  UpdateConsts c = make_update_consts(a, step, has_momentum);
+  if (OPT == SFR_OPT_SGD && step_counter) {
+    // first use of the momentum buffer (buf = clone(grad)) comes from the device counter
+    if (step == 1) c.flags |= SFR_F_SGD_FIRST_STEP; else c.flags &= ~SFR_F_SGD_FIRST_STEP;
+  }
+  fused_update_body<OPT, EMA, GT>(p, g, m, v, mask, ema, p_bf16, n, c, nullptr, sumsq);
+}
+
 // ------------------------------------------------------------------------- EMA alone
 template <int EMA>
 __global__ void __launch_bounds__(kThreads, 4)
@@ -232,6 +286,54 @@ void launch_update_ema(int ema_mode, int gt, int grid, cudaStream_t s, float* p,
   }
 }
 
+// ---- cooperative launch plumbing ---------------------------------------------------------------------
+template <int OPT, int EMA, int GT>
+cudaError_t launch_coop(int device, cudaStream_t s, float* p, void* g, float* m, float* v, const uint8_t* mask,
+                        float* ema, void* p_bf16, int64_t n, sfr_update_args a, bool has_momentum,
+                        long long* step_counter, double* sumsq) {
+  static std::atomic<int> cached[64];
+  int cap = cached[device & 63].load(std::memory_order_acquire);
+  if (cap == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, clipped_update_coop_kernel<OPT, EMA, GT>, kUpdThreads,
+                                                      0) != cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      per_sm = 1;
+    }
+    cap = per_sm * device_geometry().sm_count;
+    cached[device & 63].store(cap, std::memory_order_release);
+  }
+  const int64_t tiles = ((n >> 2) + kUpdThreads - 1) / kUpdThreads;
+  const int grid = (int)(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
+  void* args[] = {(void*)&p, (void*)&g, (void*)&m, (void*)&v, (void*)&mask, (void*)&ema, (void*)&p_bf16, (void*)&n,
+                  (void*)&a, (void*)&has_momentum, (void*)&step_counter, (void*)&sumsq};
+  return cudaLaunchCooperativeKernel((const void*)clipped_update_coop_kernel<OPT, EMA, GT>, dim3(grid),
+                                     dim3(kUpdThreads), args, 0, s);
+}
+
+template <int OPT, int EMA>
+cudaError_t launch_coop_gt(int gt, int device, cudaStream_t s, float* p, void* g, float* m, float* v,
+                           const uint8_t* mask, float* ema, void* p_bf16, int64_t n, const sfr_update_args& a,
+                           bool has_momentum, long long* step_counter, double* sumsq) {
+  if (gt == SFR_F32)
+    return launch_coop<OPT, EMA, SFR_F32>(device, s, p, g, m, v, mask, ema, p_bf16, n, a, has_momentum, step_counter, sumsq);
+  return launch_coop<OPT, EMA, SFR_BF16>(device, s, p, g, m, v, mask, ema, p_bf16, n, a, has_momentum, step_counter, sumsq);
+}
+
+template <int OPT>
+cudaError_t launch_coop_ema(int device, cudaStream_t s, float* p, void* g, float* m, float* v, const uint8_t* mask,
+                            float* ema, void* p_bf16, int64_t n, const sfr_update_args& a, bool has_momentum,
+                            long long* step_counter, double* sumsq) {
+#define SFR_COOP(E) launch_coop_gt<OPT, E>(a.g_dtype, device, s, p, g, m, v, mask, ema, p_bf16, n, a, has_momentum, step_counter, sumsq)
+  switch (a.ema_mode) {
+    case SFR_EMA_DDPM: return SFR_COOP(SFR_EMA_DDPM);
+    case SFR_EMA_DIT: return SFR_COOP(SFR_EMA_DIT);
+    case SFR_EMA_SLOWFAST: return SFR_COOP(SFR_EMA_SLOWFAST);
+    default: return SFR_COOP(SFR_EMA_NONE);
+  }
+#undef SFR_COOP
+}
+
 }  // namespace
 
 void launch_update_consts(const sfr_update_args& a, bool has_momentum, long long* step_counter,
@@ -267,6 +369,38 @@ extern "C" int sfr_masked_sumsq(const void* g, int g_dtype, const uint8_t* mask,
   SFR_LAUNCH_STATUS();
 }
 
+// One cooperative launch: zero + masked sum of squares + step-dependent scalars + K3.  The norm is LEFT in *sumsq.
+extern "C" int sfr_clipped_update(float* p, void* g, float* m, float* v, const uint8_t* mask,
+                                  float* ema, void* p_bf16, int64_t n, const sfr_update_args* a,
+                                  double* sumsq, long long* step_counter, sfr_stream_t stream) {
+  using namespace sfr;
+  SFR_REQUIRE_PTR(a);
+  SFR_REQUIRE_PTR(sumsq);
+  if (a->clip_max_norm <= 0.0) return SFR_ERR_ARG;
+  // same argument contract as sfr_fused_update (checked there as well, before anything is launched)
+  {
+    const int rc = sfr_fused_update(p, g, m, v, mask, ema, p_bf16, -2, a, sumsq, step_counter, nullptr, stream);
+    if (rc != SFR_OK) return rc;
+  }
+  if (n == 0) return SFR_OK;
+  if (n < 0) return SFR_ERR_ARG;
+  const bool has_momentum = a->opt == SFR_OPT_SGD && a->momentum != 0.0;
+  SFR_ENTER_DEVICE(p);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int dev = device_scope__.device();
+  cudaError_t e;
+  switch (a->opt) {
+    case SFR_OPT_SGD: e = launch_coop_ema<SFR_OPT_SGD>(dev, s, p, g, m, v, mask, ema, p_bf16, n, *a, has_momentum, step_counter, sumsq); break;
+    case SFR_OPT_ADAM: e = launch_coop_ema<SFR_OPT_ADAM>(dev, s, p, g, m, v, mask, ema, p_bf16, n, *a, has_momentum, step_counter, sumsq); break;
+    default: e = launch_coop_ema<SFR_OPT_ADAMW>(dev, s, p, g, m, v, mask, ema, p_bf16, n, *a, has_momentum, step_counter, sumsq); break;
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return (int)e;
+  }
+  SFR_LAUNCH_STATUS();
+}
+
 extern "C" int sfr_fused_update(float* p, void* g, float* m, float* v, const uint8_t* mask,
                                 float* ema, void* p_bf16, int64_t n,
                                 const sfr_update_args* a, const double* clip_sumsq,
@@ -274,6 +408,9 @@ extern "C" int sfr_fused_update(float* p, void* g, float* m, float* v, const uin
                                 sfr_stream_t stream) {
   using namespace sfr;
   SFR_REQUIRE_PTR(a);
+  // n == -2: validate the arguments only (sfr_clipped_update shares this contract)
+  const bool validate_only = n == -2;
+  if (validate_only) n = 1;
   if (n < 0) return SFR_ERR_ARG;
   if (a->opt < SFR_OPT_SGD || a->opt > SFR_OPT_ADAMW) return SFR_ERR_ARG;
   if (a->ema_mode < SFR_EMA_NONE || a->ema_mode > SFR_EMA_SLOWFAST) return SFR_ERR_ARG;
@@ -300,6 +437,7 @@ extern "C" int sfr_fused_update(float* p, void* g, float* m, float* v, const uin
   SFR_REQUIRE_ALIGNED(mask);
   SFR_REQUIRE_ALIGNED(ema);
   SFR_REQUIRE_ALIGNED(p_bf16);
+  if (validate_only) return SFR_OK;
   SFR_ENTER_DEVICE(p);
 
   UpdateConsts c = make_update_consts(*a, a->step, has_momentum);

@@ -67,6 +67,8 @@ class HotPath:
         # the whole select (every launch is stream-ordered, nothing is read back) replayed from one CUDA graph per
         # (buffers, n, k): the first call runs eagerly, the second captures, later ones replay.  Off when the select
         # spans ranks (its collectives are torch.distributed calls) — dist.ShardedHotPath clears the flag.
+        # clipped steps of vectors up to this size run as one cooperative launch (sfr_clipped_update)
+        self.coop_max_elems = 120_000_000
         self.select_graphs = True
         self._select_graph_cache: Dict[tuple, object] = {}
         # a saliency mask exists only once it was BUILT (ratio_mask / topk_mask) or LOADED (set_buffer / load_mask):
@@ -342,6 +344,18 @@ class HotPath:
         sgd = self.opt.kind == "sgd"
         if self.step_dev is None and sgd and self.opt.momentum != 0.0 and not self.has("m"):
             flags |= capi.F_SGD_FIRST_STEP      # torch creates momentum_buffer = clone(grad) on first use
+        sharded = type(self).reduce_scalar_ is not HotPath.reduce_scalar_
+        if max_norm is not None and not sharded and self.n <= self.coop_max_elems:
+            # small vector on one GPU: zero + norm + scalars + update as ONE cooperative launch (launch-bound otherwise)
+            self.step_count += 1
+            a = self._args(flags, ema, max_norm, lr)
+            use_ema = ema and self.ema_mode != "none"
+            capi.clipped_update(p, g, None if (sgd and self.opt.momentum == 0.0) else self.m, None if sgd else self.v,
+                                mask, self.slow if use_ema else None, a, self.sumsq, p_bf16=p_bf16,
+                                step_counter=self.step_dev)
+            self._t("masked_sumsq")
+            self._t("fused_update_ema" if use_ema else "fused_update")
+            return
         clip = None
         if max_norm is not None:
             # norm of the gradient as clip_grad_norm_ sees it: masked already (SFR-on order) or raw
