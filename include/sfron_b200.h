@@ -253,6 +253,13 @@ typedef struct sfr_update_args {
   double dampening;    /* SGD                                             */
   double ema_a;        /* mu | decay | beta, see SFR_EMA_*                */
   double clip_max_norm;/* used when clip_sumsq != NULL                    */
+  /* Learning-rate schedule on the device (optional; both NULL = use `lr`): the step's learning rate is
+   * lr_table_dev[*lr_index_dev], read by the scalar-prep kernel, so that a captured launch follows the schedule at
+   * every replay (the classification loop steps a CosineAnnealingLR each iteration: sfron.py:172-174,259).  The
+   * caller advances *lr_index_dev between iterations (any stream-ordered increment).  Requires consts_scratch_dev
+   * in sfr_fused_update. */
+  const double* lr_table_dev;
+  const long long* lr_index_dev;
 } sfr_update_args;
 
 /* consts_scratch_dev (optional, >= 128 bytes of 16-byte-aligned device memory): a one-thread prep kernel

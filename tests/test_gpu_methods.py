@@ -75,6 +75,36 @@ def test_classification_sfron_dropin(dev, tmp_path, tag):
         create_unlearn_method("SCRUB")
 
 
+@pytest.mark.parametrize("forget_freq", [1, 3])
+def test_classification_loop_replayed_from_cuda_graphs(dev, tmp_path, forget_freq):
+    """`args.cuda_graph`: every iteration (forward, backward, kernels) replayed from a CUDA graph, the per-iteration
+    cosine learning rate read on the device from torch's own scheduler table, the optimizer step counted on the
+    device.  Same model, data and seeds as the eager loop -> the same weights (sfron.py:151-260)."""
+    from sfron_b200.methods import create_unlearn_method
+    fx = load_golden("cls_sfron_default.pt")
+    finals = []
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        model = TinyNet()
+        set_flat(model, fx["theta0"], fx["names"], fx["shapes"])
+        model = model.to(dev)
+        args = argparse.Namespace(num_classes=10, seed=0, cuda_graph=graphed)
+        out_dir = tmp_path / f"g{int(graphed)}"
+        out_dir.mkdir()
+        method = create_unlearn_method("SFRon")(model, nn.CrossEntropyLoss(), str(out_dir), args)
+        method.n_iters, method.forget_freq, method.log_freq, method.ema_beta = 12, forget_freq, 10 ** 9, 0.9
+        method.prepare_unlearn(loaders(1))
+        method.get_unlearned_model()
+        torch.cuda.synchronize()
+        finals.append(torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu())
+        if graphed:
+            hp = method._hot_path().hp
+            steps = 12 + len([s for s in range(12) if s % forget_freq == 0])
+            assert int(hp.step_dev) == steps and int(hp.lr_index) == 12
+    assert (finals[0] - fx["theta0"]).abs().max() > 1e-3
+    assert close(finals[1], finals[0], 1e-6)
+
+
 def test_salun_topk_dropin(dev, tmp_path):
     from sfron_b200.methods import create_unlearn_method
     fx = load_golden("salun_topk.pt")

@@ -28,11 +28,18 @@ def test_library_exports_every_declared_symbol():
 def test_update_args_struct_matches_header():
     header = open(os.path.join(ROOT, "include", "sfron_b200.h")).read()
     body = re.search(r"typedef struct sfr_update_args \{(.*?)\} sfr_update_args;", header, flags=re.S).group(1)
-    fields = re.findall(r"^\s*(?:int32_t|uint32_t|int64_t|double)\s+(\w+);", body, flags=re.M)
+    fields = re.findall(r"^\s*(?:int32_t|uint32_t|int64_t|double|const double\*|const long long\*)\s+(\w+);", body,
+                        flags=re.M)
     assert fields == [f[0] for f in capi.UpdateArgs._fields_]
+    import ctypes
+    assert ctypes.sizeof(capi.UpdateArgs) == 4 * 4 + 8 + 9 * 8 + 2 * 8        # no padding surprises
     body = re.search(r"typedef struct sfr_select_state \{(.*?)\} sfr_select_state;", header, flags=re.S).group(1)
     fields = re.findall(r"^\s*(?:unsigned long long|uint32_t)\s+(\w+)", body, flags=re.M)
     assert fields == [f[0] for f in capi.SelectState._fields_]
+    for struct, cls in (("sfr_peer_buf", capi.PeerBuf), ("sfr_peer_geom", capi.PeerGeom)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), header, flags=re.S).group(1)
+        fields = re.findall(r"^\s*(?:void\*|int32_t|int64_t)\s+(\w+)", body, flags=re.M)
+        assert fields == [f[0] for f in cls._fields_], struct
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour WITHOUT a GPU")

@@ -107,10 +107,11 @@ def stock(model, dls, n_iters, dev):
     return t_prepare, (time.perf_counter() - t0) / n_iters
 
 
-def ours(model, dls, n_iters, dev):
+def ours(model, dls, n_iters, dev, cuda_graph=False):
     from sfron_b200.methods import create_unlearn_method
     with tempfile.TemporaryDirectory() as tmp:
-        m = create_unlearn_method("SFRon")(model, nn.CrossEntropyLoss(), tmp, argparse.Namespace(num_classes=10, seed=0))
+        m = create_unlearn_method("SFRon")(model, nn.CrossEntropyLoss(), tmp,
+                                           argparse.Namespace(num_classes=10, seed=0, cuda_graph=cuda_graph))
         m.n_iters, m.log_freq = n_iters, 10 ** 9
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -127,13 +128,18 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--batch-size", type=int, default=128)      # Classification/scripts/unlearn.sh
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="also time the loop with every iteration replayed from a CUDA graph (device-side cosine LR)")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     dls = loaders(args.batch_size, 512, 2048)
     res = {"model": "ResNet-18 harness, 11,173,962 params", "batch_size": args.batch_size, "iters": args.iters,
            "forget_batches": len(dls["forget_train"]), "retain_batches": len(dls["retain_train"])}
-    for name, fn in (("stock", stock), ("ours", ours)):
+    arms = [("stock", stock), ("ours", ours)]
+    if args.cuda_graph:
+        arms.append(("ours_cudagraph", lambda m, d, n, dv: ours(m, d, n, dv, cuda_graph=True)))
+    for name, fn in arms:
         torch.manual_seed(0)
         model = ResNet18Harness().to(dev)
         fn(deepcopy(model), dls, 10, dev)                        # warm-up (cuDNN autotune, allocator)

@@ -57,6 +57,7 @@ class UpdateArgs(C.Structure):
         ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
         ("weight_decay", C.c_double), ("momentum", C.c_double), ("dampening", C.c_double),
         ("ema_a", C.c_double), ("clip_max_norm", C.c_double),
+        ("lr_table_dev", C.c_void_p), ("lr_index_dev", C.c_void_p),
     ]
 
 

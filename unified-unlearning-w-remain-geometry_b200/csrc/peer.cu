@@ -386,12 +386,7 @@ fused_update_xchg_kernel(float* __restrict__ p, GradSrc src, float* __restrict__
   UpdateConsts c = c_arg;
   float coef_dev = 1.0f;
   if (c_dev != nullptr) {
-    if constexpr (OPT == SFR_OPT_SGD) {
-      if (c_dev->sgd_first_step) c.flags |= SFR_F_SGD_FIRST_STEP; else c.flags &= ~SFR_F_SGD_FIRST_STEP;
-    } else {
-      c.neg_step_size = c_dev->neg_step_size;
-      c.bc2_sqrt = c_dev->bc2_sqrt;
-    }
+    apply_dev_consts<OPT>(c, c_dev);
     coef_dev = c_dev->clip_coef;
   }
   constexpr bool kHasV = OPT != SFR_OPT_SGD;
@@ -706,7 +701,8 @@ extern "C" int sfr_peer_fused_update(float* p, const float* g_red, const sfr_pee
   UpdateConsts c = make_update_consts(*a, a->step, has_momentum);
   const DevConsts* c_dev = nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (step_counter != nullptr) SFR_REQUIRE_PTR(consts_scratch);
+  if ((a->lr_table_dev == nullptr) != (a->lr_index_dev == nullptr)) return SFR_ERR_NULL;
+  if (step_counter != nullptr || a->lr_table_dev != nullptr) SFR_REQUIRE_PTR(consts_scratch);
   if (consts_scratch != nullptr) {
     if (!aligned16(consts_scratch)) return SFR_ERR_ALIGN;
     launch_update_consts(*a, has_momentum, step_counter, clip_sumsq, consts_scratch, s);

@@ -110,13 +110,7 @@ fused_update_body(float* __restrict__ p, void* __restrict__ g, float* __restrict
   UpdateConsts c = c_arg;
   float coef_dev = 1.0f;
   if (c_dev != nullptr) {
-    if constexpr (OPT == SFR_OPT_SGD) {
-      // only SGD's momentum-buffer init changes WHICH loads are issued (read_m below)
-      if (c_dev->sgd_first_step) c.flags |= SFR_F_SGD_FIRST_STEP; else c.flags &= ~SFR_F_SGD_FIRST_STEP;
-    } else {
-      c.neg_step_size = c_dev->neg_step_size;
-      c.bc2_sqrt = c_dev->bc2_sqrt;
-    }
+    apply_dev_consts<OPT>(c, c_dev);
     coef_dev = c_dev->clip_coef;
   }
   constexpr bool kHasV = OPT != SFR_OPT_SGD;
@@ -216,6 +210,7 @@ clipped_update_coop_kernel(float* __restrict__ p, void* __restrict__ g, float* _
   else masked_sumsq_body<GT, false, kUpdThreads>(g, mask, n, sumsq);
   grid.sync();
   const long long step = step_counter ? *step_counter : (long long)a.step;
+  resolve_lr(a);
   UpdateConsts c = make_update_consts(a, step, has_momentum);
   if (OPT == SFR_OPT_SGD && step_counter) {
     // first use of the momentum buffer (buf = clone(grad)) comes from the device counter
@@ -253,8 +248,12 @@ __global__ void update_consts_kernel(sfr_update_args a, bool has_momentum, long 
                                      const double* clip_sumsq, DevConsts* out) {
   // optimizer state['step'] lives on the device when a counter is given (graph replay)
   const long long step = step_counter ? ++(*step_counter) : (long long)a.step;
+  resolve_lr(a);
   const UpdateConsts c = make_update_consts(a, step, has_momentum);
   DevConsts d;
+  d.neg_lr = c.neg_lr;
+  d.decay_mul = c.decay_mul;
+  d.has_lr = a.lr_table_dev != nullptr;
   d.neg_step_size = c.neg_step_size;
   d.bc2_sqrt = c.bc2_sqrt;
   d.clip_coef = clip_sumsq ? clip_coef_from_sumsq(clip_sumsq, (float)a.clip_max_norm) : 1.0f;
@@ -443,7 +442,8 @@ extern "C" int sfr_fused_update(float* p, void* g, float* m, float* v, const uin
   UpdateConsts c = make_update_consts(*a, a->step, has_momentum);
   const DevConsts* c_dev = nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (step_counter != nullptr) SFR_REQUIRE_PTR(consts_scratch);
+  if ((a->lr_table_dev == nullptr) != (a->lr_index_dev == nullptr)) return SFR_ERR_NULL;
+  if (step_counter != nullptr || a->lr_table_dev != nullptr) SFR_REQUIRE_PTR(consts_scratch);
   if (consts_scratch != nullptr) {
     // one-thread prep kernel: step-dependent scalars (from the device counter if given: graph
     // replay) and the clip coefficient, precomputed so the main kernel never stalls on them

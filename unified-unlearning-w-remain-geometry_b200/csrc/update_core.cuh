@@ -47,7 +47,29 @@ struct DevConsts {
   float bc2_sqrt;
   float clip_coef;
   uint32_t sgd_first_step;
+  float neg_lr;       // the learning-rate-dependent scalars, valid when has_lr (device-side schedule)
+  float decay_mul;
+  uint32_t has_lr;
 };
+
+// Scalars a kernel must take from the device copy instead of its by-value UpdateConsts.
+template <int OPT>
+__device__ __forceinline__ void apply_dev_consts(UpdateConsts& c, const DevConsts* c_dev) {
+  if constexpr (OPT == SFR_OPT_SGD) {
+    // only SGD's momentum-buffer init changes WHICH loads are issued
+    if (c_dev->sgd_first_step) c.flags |= SFR_F_SGD_FIRST_STEP; else c.flags &= ~SFR_F_SGD_FIRST_STEP;
+    if (c_dev->has_lr) c.neg_lr = c_dev->neg_lr;
+  } else {
+    c.neg_step_size = c_dev->neg_step_size;
+    c.bc2_sqrt = c_dev->bc2_sqrt;
+    if (c_dev->has_lr) c.decay_mul = c_dev->decay_mul;
+  }
+}
+
+// The step's learning rate: from the device-side schedule when one is attached.
+__device__ __forceinline__ void resolve_lr(sfr_update_args& a) {
+  if (a.lr_table_dev != nullptr) a.lr = a.lr_table_dev[*a.lr_index_dev];
+}
 
 // ---- slow / EMA weights ----------------------------------------------------------------
 // Returns the new slow value; may rewrite p (SLOWFAST).

@@ -353,7 +353,8 @@ class ShardedHotPath(HotPath):
             ema=self.slow if use_ema else None, bc_f32=None if weights is None else weights.buf,
             bc_bf16=None if weights_bf16 is None else weights_bf16.buf, bc_transport=x.push_transport, clip_sumsq=clip,
             step_counter=self.step_dev,
-            consts_scratch=self._consts_dev if (clip is not None or self.step_dev is not None) else None)
+            consts_scratch=self._consts_dev if (clip is not None or self.step_dev is not None
+                                                or self.lr_table is not None) else None)
         self._t("fused_update_ema" if use_ema else "fused_update")
         x.barrier()                                       # gradients may be overwritten; every weight store has landed
 

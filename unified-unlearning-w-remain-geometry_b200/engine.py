@@ -67,6 +67,9 @@ class HotPath:
         # the whole select (every launch is stream-ordered, nothing is read back) replayed from one CUDA graph per
         # (buffers, n, k): the first call runs eagerly, the second captures, later ones replay.  Off when the select
         # spans ranks (its collectives are torch.distributed calls) — dist.ShardedHotPath clears the flag.
+        # device-side learning-rate schedule (set_lr_schedule): table of per-iteration rates + the iteration index
+        self.lr_table: Optional[torch.Tensor] = None
+        self.lr_index: Optional[torch.Tensor] = None
         # clipped steps of vectors up to this size run as one cooperative launch (sfr_clipped_update)
         self.coop_max_elems = 120_000_000
         self.select_graphs = True
@@ -102,6 +105,17 @@ class HotPath:
             self.buffer("v")
         if self.ema_mode != "none":
             self.buffer("slow")
+
+    def set_lr_schedule(self, rates: Sequence[float]) -> None:
+        """Learning rate per ITERATION, kept on the device: every step reads `rates[lr_index]` in its scalar-prep
+        kernel, so a CUDA graph of one iteration follows the schedule at every replay (the classification loop's
+        per-iteration CosineAnnealingLR, sfron.py:172-174,259).  `advance_lr()` moves to the next iteration."""
+        self.lr_table = torch.tensor(list(rates), dtype=torch.float64, device=self.device)
+        self.lr_index = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+    def advance_lr(self) -> None:
+        """scheduler.step(): stream-ordered, capturable."""
+        self.lr_index.add_(1)
 
     # ---- lazily allocated role buffers ------------------------------------------------------------
     def buffer(self, role: str, dtype=torch.float32) -> torch.Tensor:
@@ -329,6 +343,8 @@ class HotPath:
         a.weight_decay, a.momentum, a.dampening = o.weight_decay, o.momentum, o.dampening
         a.ema_a = self.ema_a
         a.clip_max_norm = 0.0 if max_norm is None else max_norm
+        if self.lr_table is not None and lr is None:
+            a.lr_table_dev, a.lr_index_dev = self.lr_table.data_ptr(), self.lr_index.data_ptr()
         return a
 
     def _step(self, p: torch.Tensor, g: torch.Tensor, *, mask: Optional[torch.Tensor], mask_order: str,
@@ -372,7 +388,8 @@ class HotPath:
                           clip_sumsq=clip, p_bf16=p_bf16, step_counter=self.step_dev,
                           # the prep kernel pays off when there is a clip coefficient to precompute or a
                           # device step counter to advance; otherwise everything goes by value
-                          consts_scratch=self._consts_dev if (clip is not None or self.step_dev is not None) else None)
+                          consts_scratch=self._consts_dev if (clip is not None or self.step_dev is not None
+                                                              or self.lr_table is not None) else None)
         self._t("fused_update_ema" if use_ema else "fused_update")
 
     def forget_step(self, p: torch.Tensor, g: torch.Tensor, *, mask: Optional[torch.Tensor] = None,

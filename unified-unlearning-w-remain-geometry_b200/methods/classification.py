@@ -98,6 +98,9 @@ class SFRon(UnlearnMethod):
         self.mask = True
         self.th = 1
         self.log_freq = 500
+        # extension: replay whole iterations (forward, backward, kernels) from CUDA graphs — the loop is launch-bound
+        # at ResNet-18 size.  The per-iteration cosine learning rate then lives on the device (HotPath.set_lr_schedule).
+        self.cuda_graph = bool(getattr(args, "cuda_graph", False))
         self._mhp: Optional[ModelHotPath] = None
 
     # ---- flat state, created on first use (hyper-parameters may be edited after __init__) ---------
@@ -164,6 +167,13 @@ class SFRon(UnlearnMethod):
         if self.ema_enabled:
             mhp.hp.init_slow(mhp.flat.p)              # ori_model = deepcopy(self.model)
         mhp.zero_grad()
+        if self.cuda_graph:
+            rates = []
+            for _ in range(self.n_iters):             # torch's own scheduler -> the exact per-iteration rates
+                rates.append(dummy.param_groups[0]["lr"])
+                dummy.step()
+                scheduler.step()
+            return self._unlearn_graphed(mhp, rates, lr_scheduler, forget_train_iter, retain_train_iter)
         log_forget = log_remain = 0
         run_forget = run_remain = 0.0
         start_time = time.time()
@@ -201,6 +211,96 @@ class SFRon(UnlearnMethod):
                 start_time = time.time()
             dummy.step()          # no-op (the dummy has no gradient); keeps torch's step-order check quiet
             scheduler.step()
+        return self.model
+
+    def _unlearn_graphed(self, mhp, rates, alpha_scheduler, forget_iter, retain_iter) -> nn.Module:
+        """The loop of get_unlearned_model with every iteration replayed from a CUDA graph: one graph for the
+        iterations that start with a forget step (step % forget_freq == 0), one for the others.  Batches live in
+        static tensors refilled before each replay; alpha_t is a device scalar; the learning rate of the iteration is
+        read on the device from the scheduler's table and the optimizer step count lives on the device too.  A batch
+        of another shape (a ragged last batch) runs that iteration eagerly — same kernels, same device-side state."""
+        hp, flat, dev = mhp.hp, mhp.flat, mhp.flat.device
+        if not flat.grads_as_views:
+            raise RuntimeError("cuda_graph=True needs view-gradients (FlatParams(grads_as_views=True))")
+        hp.set_lr_schedule(rates)
+        hp.enable_graph_replay()
+        alpha_dev = torch.zeros((), dtype=torch.float32, device=dev)
+        xf, yf = (t.to(dev).clone() for t in next(forget_iter))
+        xr, yr = (t.to(dev).clone() for t in next(retain_iter))
+        pending = {"forget": (xf.clone(), yf.clone()), "retain": (xr.clone(), yr.clone())}   # already drawn: used first
+
+        def forget_part():
+            self.model.train()
+            (alpha_dev * -self.forget_loss_function(self.model(xf), yf)).backward()
+            mhp.forget_step(use_mask=bool(self.mask), max_norm=self.max_norm)            # sfron.py:201-206
+
+        def retain_part():
+            self.model.train()
+            self.retain_loss_function(self.model(xr), yr).backward()
+            mhp.remain_step(ema=self.ema_enabled)                                        # :222,255-257
+            hp.advance_lr()                                                              # scheduler.step() :259
+
+        bodies = {True: lambda: (forget_part(), retain_part()), False: retain_part}
+        # one eager pass per body outside the capture (cuDNN / cuBLAS choose algorithms there), state put back after
+        roles = [r for r in ("m", "slow") if hp.has(r)] + (["v"] if hp.has("v") else [])
+        saved = {r: hp.buffer(r).clone() for r in roles}
+        saved_p, saved_step, saved_idx = flat.p.clone(), hp.step_dev.clone(), hp.lr_index.clone()
+        saved_buffers = {k: b.clone() for k, b in self.model.named_buffers()}
+        saved_count = hp.step_count
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for with_forget in ((True, False) if self.forget_freq > 1 else (True,)):
+                bodies[with_forget]()
+        torch.cuda.current_stream(dev).wait_stream(side)
+
+        def restore():
+            for r in roles:
+                hp.buffer(r).copy_(saved[r])
+            flat.p.copy_(saved_p)
+            hp.step_dev.copy_(saved_step)
+            hp.lr_index.copy_(saved_idx)
+            for k, b in self.model.named_buffers():
+                b.copy_(saved_buffers[k])
+            hp.step_count = saved_count
+            mhp.zero_grad()
+
+        restore()
+        graphs = {}
+        for with_forget in ((True, False) if self.forget_freq > 1 else (True,)):
+            graphs[with_forget] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graphs[with_forget]):
+                bodies[with_forget]()
+        restore()                                          # capture records only, but host-side counters moved
+        for step in range(self.n_iters):
+            with_forget = step % self.forget_freq == 0
+            static_ok = True
+            if with_forget:
+                alpha_dev.fill_(alpha_scheduler(self.forget_alpha, step, self.n_iters))
+                bx, by = pending.pop("forget", None) or next(forget_iter)
+                static_ok &= tuple(bx.shape) == tuple(xf.shape)
+                if static_ok:
+                    xf.copy_(bx, non_blocking=True)
+                    yf.copy_(by, non_blocking=True)
+            rx, ry = pending.pop("retain", None) or next(retain_iter)
+            static_ok &= tuple(rx.shape) == tuple(xr.shape)
+            if static_ok:
+                xr.copy_(rx, non_blocking=True)
+                yr.copy_(ry, non_blocking=True)
+                graphs[with_forget].replay()
+            else:                                          # ragged batch: the same iteration, launched eagerly
+                self.model.train()
+                if with_forget:
+                    bx, by = bx.to(dev), by.to(dev)
+                    (alpha_dev * -self.forget_loss_function(self.model(bx), by)).backward()
+                    mhp.forget_step(use_mask=bool(self.mask), max_norm=self.max_norm)
+                rx, ry = rx.to(dev), ry.to(dev)
+                self.retain_loss_function(self.model(rx), ry).backward()
+                mhp.remain_step(ema=self.ema_enabled)
+                hp.advance_lr()
+            if self.eval and (step + 1) % self.log_freq == 0 and self.validate_fn is not None:
+                self.validate_fn(self.model)
+        hp.step_count = int(hp.step_dev)
         return self.model
 
     def get_params(self) -> dict:
