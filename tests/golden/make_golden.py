@@ -162,6 +162,151 @@ def classification(tag, ema_beta, n_iters=10, forget_freq=3):
     print("wrote", tag, "N =", theta0.numel(), "loop records", len(loop))
 
 
+# ------------------------------------------------------------------------------- the REAL reference networks
+def _slice_fixture(names, shapes, grads_per_backward, files, small=8192):
+    """Everything needed to pin names / order / shapes / dtypes for ALL tensors, and full inputs + outputs for the
+    tensors of at most `small` elements (biases, norms, embeddings, the classifier): a fixture of a few hundred KB out
+    of vectors of 11 M / 38.6 M elements."""
+    sub = [n for n in names if torch.tensor(shapes[n]).prod().item() <= small]
+    out = dict(names=names, shapes=shapes, small_names=sub,
+               grads=[{n: g[n].clone() for n in sub} for g in grads_per_backward])
+    for key, d in files.items():
+        out[key] = {n: (d[n].clone() if torch.is_tensor(d[n]) else d[n]) for n in sub}
+        out[key + "_dtype"] = str(next(v for v in d.values() if torch.is_tensor(v)).dtype)
+        out[key + "_keys"] = list(d.keys())
+        out[key + "_sum64"] = {n: (float(d[n].double().sum()) if torch.is_tensor(d[n]) else None) for n in names}
+    return out
+
+
+class DictGradRecorder:
+    """Per-backward dict name -> raw gradient, through tensor hooks on the real module's parameters."""
+
+    def __init__(self, named_params):
+        self.names = [n for n, _ in named_params]
+        self.records, self._cur = [], {}
+        for n, p in named_params:
+            p.register_hook(self._hook(n))
+
+    def _hook(self, name):
+        def fn(grad):
+            self._cur[name] = grad.detach().clone()
+            if len(self._cur) == len(self.names):
+                self.records.append(self._cur)
+                self._cur = {}
+        return fn
+
+
+def real_models():
+    """Config 1 and config 2 on the reference's OWN networks (Classification/models/resnet.py:ResNet18, 11,173,962
+    parameters in 62 tensors; DDPM/models/diffusion.py:Conditional_Model at the shipped cifar10_sfron.yml, 38,632,323
+    parameters in 334 tensors): `SFRon.get_weight_saliency_mask` and `Diffusion.generate_fisher()` +
+    generate_fisher_mask.py executed whole on two tiny synthetic batches per set.  The fixture keeps the key lists of
+    the files the reference wrote, per-tensor fp64 checksums of every Fisher tensor, and — for the tensors of at most
+    8192 elements — the recorded gradients, Fisher values and mask bits in full."""
+    from torch.utils.data import DataLoader, TensorDataset
+    fixture = {}
+    # ---- config 1: ResNet-18 ------------------------------------------------------------------------------
+    unlearn = import_classification()
+    from models.resnet import ResNet18
+    torch.manual_seed(0)
+    model = ResNet18(10)
+    names = [n for n, _ in model.named_parameters()]
+    shapes = {n: list(p.shape) for n, p in model.named_parameters()}
+    rec = DictGradRecorder(list(model.named_parameters()))
+    g = torch.Generator().manual_seed(41)
+    mk = lambda k: DataLoader(TensorDataset(torch.randn(k, 3, 32, 32, generator=g), torch.randint(0, 10, (k,), generator=g)),
+                              batch_size=4, shuffle=False)
+    with tempfile.TemporaryDirectory() as tmp:
+        method = unlearn.create_unlearn_method("SFRon")(model, nn.CrossEntropyLoss(), tmp, argparse.Namespace(num_classes=10, seed=0))
+        mask = method.get_weight_saliency_mask(mk(8), mk(8), 1.0)                 # sfron.py:262-336
+        ff, rf = torch.load(os.path.join(tmp, "forget_fisher.pt")), torch.load(os.path.join(tmp, "remain_fisher.pt"))
+    assert len(rec.records) == 4 and sum(p.numel() for p in model.parameters()) == 11_173_962 and len(names) == 62
+    fixture["resnet18"] = _slice_fixture(names, shapes, rec.records, dict(forget_fisher=ff, remain_fisher=rf, mask=mask))
+    fixture["resnet18"].update(n_forget=2, n_remain=2, threshold=1.0, total=11_173_962,
+                               mask_zero_total=int(sum(m.numel() - m.count_nonzero() for m in mask.values())))
+    for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+        del sys.modules[k]                                                         # DDPM has its own `models` package
+    sys.path.remove(os.path.join(REF, "Classification"))
+    # ---- config 2: DDPM Conditional_Model -------------------------------------------------------------------
+    sys.path.insert(0, os.path.join(REF, "DDPM"))
+    import runners.diffusion as RD
+
+    def d2n(d):
+        ns = argparse.Namespace()
+        for k, v in d.items():
+            setattr(ns, k, d2n(v) if isinstance(v, dict) else v)
+        return ns
+
+    cfg = yaml.safe_load(open(os.path.join(REF, "DDPM/configs/cifar10_sfron.yml")))
+    cfg["training"].update(log_freq=10 ** 9, gamma=1.0, lmbda=1.0)
+    config = d2n(cfg)
+    g = torch.Generator().manual_seed(42)
+    mkd = lambda labels: DataLoader(TensorDataset(torch.rand(len(labels), 3, 32, 32, generator=g), torch.tensor(labels)),
+                                    batch_size=2, shuffle=False)
+    remain_loader, forget_loader = mkd([3, 7, 1, 9]), mkd([0, 0, 0, 0])
+    RD.get_forget_dataset = lambda args, config, label: (remain_loader, forget_loader)
+    created = []
+    real_ctor = RD.Conditional_Model
+
+    def ctor(cfg_):
+        m = real_ctor(cfg_)
+        created.append(m)
+        return m
+
+    RD.Conditional_Model = ctor
+    torch.manual_seed(43)
+    init = nn.DataParallel(real_ctor(config))
+    pnames = [n for n, _ in init.named_parameters()]
+    pshapes = {n: list(p.shape) for n, p in init.named_parameters()}
+    assert sum(p.numel() for p in init.parameters()) == 38_632_323 and len(pnames) == 334
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "ckpts"))
+        torch.save([init.state_dict(), {}, 0, {}], os.path.join(tmp, "ckpts/ckpt.pth"))
+        args = argparse.Namespace(ckpt_folder=tmp, label_to_forget=0, cond_scale=2.0)
+        runner = RD.Diffusion(args, config)
+        recs = []
+        orig_backward = torch.Tensor.backward
+
+        def backward(tensor, *a, **k):
+            out = orig_backward(tensor, *a, **k)
+            recs.append({"module." + n: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p))
+                         for n, p in created[-1].named_parameters()})
+            return out
+
+        torch.Tensor.backward = backward
+        clip_norms = []
+        orig_clip = torch.nn.utils.clip_grad_norm_
+
+        def clip(params, max_norm, *a, **k):
+            total = orig_clip(params, max_norm, *a, **k)       # the fp32 norm of per-tensor norms the reference clips by
+            clip_norms.append(total.detach().clone())
+            return total
+
+        torch.nn.utils.clip_grad_norm_ = clip
+        try:
+            torch.manual_seed(44)
+            runner.generate_fisher()                                               # runners/diffusion.py:1210-1364
+        finally:
+            torch.Tensor.backward = orig_backward
+            torch.nn.utils.clip_grad_norm_ = orig_clip
+        mdir = os.path.join(tmp, "mask_0")
+        subprocess.run([sys.executable, os.path.join(REF, "DDPM/generate_fisher_mask.py"), "--ckpt_folder", mdir,
+                        "--threshold", "1.0"], check=True, stdout=subprocess.DEVNULL)
+        ff, rf = torch.load(os.path.join(mdir, "forget_fisher.pt")), torch.load(os.path.join(mdir, "remain_fisher.pt"))
+        mask = torch.load(os.path.join(mdir, "fisher_1.0.pt"))
+    assert len(recs) == 4 and list(ff.keys()) == pnames
+    fixture["ddpm"] = _slice_fixture(pnames, pshapes, recs, dict(forget_fisher=ff, remain_fisher=rf, mask=mask))
+    # the Fisher is of the CLIPPED batch gradient: the clip coefficient needs the norm over ALL tensors
+    assert len(clip_norms) == 4
+    fixture["ddpm"].update(n_forget=2, n_remain=2, threshold=1.0, total=38_632_323, grad_clip=config.optim.grad_clip,
+                           torch_total_norms=torch.stack(clip_norms).float(),
+                           grad_norms=[float(torch.sqrt(sum(v.double().pow(2).sum() for v in r.values()))) for r in recs],
+                           mask_zero_total=int(sum(m.numel() - m.count_nonzero() for m in mask.values())))
+    torch.save(fixture, os.path.join(OUT, "real_models.pt"))
+    print("wrote real_models.pt:", {k: (len(v["names"]), len(v["small_names"])) for k, v in fixture.items()},
+          os.path.getsize(os.path.join(OUT, "real_models.pt")) // 1024, "KiB")
+
+
 def salun_topk():
     unlearn = import_classification()
     out = {}
@@ -1083,6 +1228,7 @@ PARTS = {
     "dit_loop": dit_loop,
     "dit_scripts": dit_scripts,
     "sd_scripts": sd_scripts,
+    "real_models": real_models,
 }
 
 if __name__ == "__main__":

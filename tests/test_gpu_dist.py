@@ -204,9 +204,12 @@ def _peer_exchange(rank, world, dev):
             gb = O.dp_reduce([(t * 100).to(g_dtype) for t in gf])
             acc = {"w": torch.zeros(n)}
             O.fisher_accumulate_clipped(acc, {"w": gb}, 3.0, 1.0)
-            # Fisher of the clipped gradient = coef**2 * g**2 / L: torch's fp32 norm-of-norms is itself off by up
-            # to ~1e-6 relative at a million elements (ours accumulates in double), and the square doubles it
-            assert _close(hp.remain_fisher, sg.local(acc["w"]), 1e-2 if g_dtype == torch.bfloat16 else 4e-6), \
+            # Fisher of the clipped gradient = coef**2 * g**2 / L: torch's CPU fp32 norm of a million-element tensor
+            # is itself ~1e-5 off the exact norm (measured below; ours accumulates in double), and the square doubles it
+            exact = gb.double().pow(2).sum().sqrt().item()
+            norm_err = abs(float(O.clip_grad_norm([gb.clone()], 1e30)) - exact) / exact
+            assert _close(hp.remain_fisher, sg.local(acc["w"]),
+                          1e-2 if g_dtype == torch.bfloat16 else 1e-6 + 2.5 * norm_err), \
                 f"{name}/{g_dtype}: clipped Fisher, max rel err " \
                 f"{((hp.remain_fisher.cpu() - sg.local(acc['w'])).abs() / sg.local(acc['w']).abs().clamp_min(1e-30)).max()}"
     # ---- the barrier's payload: sum over ranks in rank order, identical bits everywhere

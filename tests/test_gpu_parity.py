@@ -119,13 +119,18 @@ def test_saliency_accumulate_matches_clip_then_add(sfr, dev, n):
     assert bits_equal(hp.buffer("grad_sum").cpu(), acc_ref)
     hp.buffer("grad_sum").zero_()
     acc_ref = torch.zeros(n)
+    norm_err = 0.0
     for scale in (5.0, 1e-4, 2.0):                      # norms above and below max_norm
         x = torch.randn(n, generator=g) * scale
         y = x.clone()
-        O.clip_grad_norm([y], 1.0)
+        tn = float(O.clip_grad_norm([y], 1.0))
+        exact = x.double().pow(2).sum().sqrt().item()
+        norm_err = max(norm_err, abs(tn - exact) / exact)
         acc_ref += y
         hp.saliency_accumulate(x.to(dev), clip_max_norm=1.0)
-    assert close(hp.buffer("grad_sum"), acc_ref)
+    # torch's CPU fp32 norm of ONE million-element tensor is itself ~1e-5 off the exact norm (measured here, and it
+    # depends on the host's thread count); the kernel's norm accumulates in double.  The bar is 1e-6 beyond that.
+    assert close(hp.buffer("grad_sum"), acc_ref, RTOL + 1.5 * norm_err), norm_err
 
 
 def test_k1_bf16_gradients(sfr, dev):

@@ -202,3 +202,39 @@ def test_k3_ddpm_adam_clip_ema_10_iterations(sfr, dev):
     record(test="k3", config="ddpm", n=n, tensors=len(shapes), optimizer_steps=2 * iters, **st)
     assert close(p, want), st
     assert close(hp.slow, ref.flat("slow")) and close(hp.m, ref.flat("m")) and close(hp.v, ref.flat("v"))
+
+
+@pytest.mark.parametrize("which", ["resnet18", "ddpm"])
+def test_real_reference_networks_slices_through_the_kernels(sfr, dev, which):
+    """Golden real_models.pt (the reference's own ResNet18 / Conditional_Model, its own methods executed whole): the
+    recorded gradients of the tensors of <= 8192 elements go through K1 (with the reference's own clip norm for DDPM)
+    and K2a on a flat sub-vector — Fisher and mask bit-exact — and the exporters reproduce the reference's key list."""
+    from conftest import load_golden
+    fx = load_golden("real_models.pt")[which]
+    small = fx["small_names"]
+    layout = sfr.FlatLayout([(n, fx["shapes"][n]) for n in small])
+    n = layout.numel
+    hp = sfr.HotPath(n, dev, sfr.OptConfig())
+    nf, nr = fx["n_forget"], fx["n_remain"]
+    for role, recs, count, base in (("forget", fx["grads"][:nf], nf, 0), ("remain", fx["grads"][nf:], nr, nf)):
+        acc = hp.buffer(f"{role}_fisher")
+        acc.zero_()
+        for i, g in enumerate(recs):
+            flat_g = layout.flatten(g, dtype=torch.float32).to(dev)
+            if which == "ddpm":
+                # the clip norm spans ALL 334 tensors: feed the one the reference computed (fp32); its square is exact
+                # in double, so the kernel's coefficient is the reference's bit for bit
+                total = fx["torch_total_norms"][base + i].double()
+                sfr.capi.fisher_accum(acc, flat_g, float(count), clip_sumsq=(total * total).reshape(1).to(dev),
+                                      clip_max_norm=fx["grad_clip"])
+            else:
+                sfr.capi.fisher_accum(acc, flat_g, float(count))
+        want = layout.flatten(fx[f"{role}_fisher"], dtype=torch.float32)
+        assert bits_equal(acc.cpu(), want), role
+    mask = hp.ratio_mask(fx["threshold"])
+    want = layout.flatten({k: v.to(torch.uint8) for k, v in fx["mask"].items()}, dtype=torch.uint8)
+    assert torch.equal(mask.cpu(), want)
+    d = sfr.formats.ratio_mask_to_dict(layout, mask, all_names=small)
+    assert list(d.keys()) == small and all(d[k].dtype == torch.bool and list(d[k].shape) == fx["shapes"][k] for k in small)
+    record(test="real_reference_slices", config=which, tensors=len(small), of=len(fx["names"]), elements=n,
+           result="K1 / K2a bit-exact vs the reference's own networks")

@@ -3,7 +3,9 @@ tests/golden/make_golden.py from /root/reference).  CPU only."""
 import pytest
 import torch
 
-from conftest import bits_equal, load_golden, max_rel_err, unflat
+import os
+
+from conftest import ROOT, bits_equal, load_golden, max_rel_err, unflat
 from oracle import sfron_oracle as O
 
 RTOL = 1e-6  # north-star tolerance for fp32 values; masks must be bit-exact
@@ -304,3 +306,42 @@ def test_ddpm_save_fim_executed_whole():
         O.per_sample_fim(acc, [unflat(r, names, shapes) for r in rows], fx["dataset_len"])
     got = torch.cat([acc[n].reshape(-1) for n in names])
     assert bits_equal(got, fx["fim"])
+
+
+# ------------------------------------------------------------------ the reference's REAL networks (configs 1 and 2)
+def _clip_coef(total_norm, max_norm):
+    """clip_grad_norm_'s coefficient from the fp32 total norm the reference computed (torch/nn/utils/clip_grad.py)."""
+    return torch.clamp(torch.tensor(max_norm, dtype=torch.float32) / (total_norm + 1e-6), max=1.0)
+
+
+@pytest.mark.parametrize("which", ["resnet18", "ddpm"])
+def test_real_reference_networks_fisher_and_mask_slices(which):
+    """real_models.pt: SFRon.get_weight_saliency_mask on the reference's ResNet18 and Diffusion.generate_fisher +
+    generate_fisher_mask.py on its Conditional_Model, executed whole.  Key lists / order / prefixes of the files are
+    pinned for ALL tensors; for the tensors of <= 8192 elements the oracle reproduces Fisher and mask bit for bit."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    fx = load_golden("real_models.pt")[which]
+    names, small = fx["names"], fx["small_names"]
+    with torch.device("meta"):
+        if which == "resnet18":
+            from resnet18_cifar import ResNet18Harness
+            harness, prefix = ResNet18Harness(), ""
+        else:
+            from ddpm_unet import DDPMCondUNet
+            harness, prefix = DDPMCondUNet(), "module."
+    assert [(prefix + n, list(p.shape)) for n, p in harness.named_parameters()] == [(n, fx["shapes"][n]) for n in names]
+    assert fx["forget_fisher_keys"] == names == fx["remain_fisher_keys"] == fx["mask_keys"]
+    assert fx["forget_fisher_dtype"] == "torch.float32" and fx["mask_dtype"] == "torch.bool"
+    nf, nr = fx["n_forget"], fx["n_remain"]
+    for role, recs, count in (("forget_fisher", fx["grads"][:nf], nf), ("remain_fisher", fx["grads"][nf:], nr)):
+        acc = O.fisher_init(small)
+        for i, g in enumerate(recs):
+            if which == "ddpm":                                   # Fisher of the CLIPPED gradient (:1270-1281)
+                coef = _clip_coef(fx["torch_total_norms"][i if role == "forget_fisher" else nf + i], fx["grad_clip"])
+                g = {n: t * coef for n, t in g.items()}
+            O.fisher_accumulate(acc, g, count)
+        for n in small:
+            assert bits_equal(acc[n], fx[role][n]), (role, n)
+    mask, _, _ = O.ratio_mask(fx["forget_fisher"], fx["remain_fisher"], fx["threshold"])
+    assert all(torch.equal(mask[n], fx["mask"][n]) for n in small)
