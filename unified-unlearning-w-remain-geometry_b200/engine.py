@@ -349,7 +349,10 @@ class HotPath:
 
     def _step(self, p: torch.Tensor, g: torch.Tensor, *, mask: Optional[torch.Tensor], mask_order: str,
               max_norm: Optional[float], ema: bool, lr: Optional[float], zero_grad: bool,
-              p_bf16: Optional[torch.Tensor]) -> None:
+              p_bf16: Optional[torch.Tensor], norm_sq: Optional[torch.Tensor] = None) -> None:
+        """norm_sq (device float64[1]): the squared gradient norm to clip by, when the caller already has it (a norm
+        reduced elsewhere; the parity tests feed the reference's own fp32 norm to isolate the update arithmetic
+        from torch's CPU norm error).  Default: computed here by the masked sum-of-squares kernel."""
         flags = 0
         if mask is not None:
             flags |= capi.F_MASK if mask_order == "mask_then_clip" else capi.F_MASK_AFTER_CLIP
@@ -361,7 +364,7 @@ class HotPath:
         if self.step_dev is None and sgd and self.opt.momentum != 0.0 and not self.has("m"):
             flags |= capi.F_SGD_FIRST_STEP      # torch creates momentum_buffer = clone(grad) on first use
         sharded = type(self).reduce_scalar_ is not HotPath.reduce_scalar_
-        if max_norm is not None and not sharded and self.n <= self.coop_max_elems:
+        if max_norm is not None and norm_sq is None and not sharded and self.n <= self.coop_max_elems:
             # small vector on one GPU: zero + norm + scalars + update as ONE cooperative launch (launch-bound otherwise)
             self.step_count += 1
             a = self._args(flags, ema, max_norm, lr)
@@ -373,7 +376,11 @@ class HotPath:
             self._t("fused_update_ema" if use_ema else "fused_update")
             return
         clip = None
-        if max_norm is not None:
+        if max_norm is not None and norm_sq is not None:
+            self.sumsq.copy_(norm_sq.reshape(1))
+            self._t("masked_sumsq")
+            clip = self.sumsq
+        elif max_norm is not None:
             # norm of the gradient as clip_grad_norm_ sees it: masked already (SFR-on order) or raw
             self.sumsq.zero_()
             capi.masked_sumsq(g, mask if (mask is not None and mask_order == "mask_then_clip") else None, self.sumsq)
@@ -395,21 +402,21 @@ class HotPath:
     def forget_step(self, p: torch.Tensor, g: torch.Tensor, *, mask: Optional[torch.Tensor] = None,
                     use_mask: bool = True, max_norm: Optional[float] = None, lr: Optional[float] = None,
                     mask_order: str = "mask_then_clip", zero_grad: bool = False,
-                    p_bf16: Optional[torch.Tensor] = None) -> None:
+                    p_bf16: Optional[torch.Tensor] = None, norm_sq: Optional[torch.Tensor] = None) -> None:
         """grad *= mask ; clip_grad_norm_(max_norm) ; optimizer.step()
         (sfron.py:201-206; runners/diffusion.py:1126-1138; DiT/forget.py:289-299)."""
         if mask is None and use_mask:
             mask = self.require_mask()
         self._step(p, g, mask=mask if use_mask else None, mask_order=mask_order, max_norm=max_norm,
-                   ema=False, lr=lr, zero_grad=zero_grad, p_bf16=p_bf16)
+                   ema=False, lr=lr, zero_grad=zero_grad, p_bf16=p_bf16, norm_sq=norm_sq)
 
     def remain_step(self, p: torch.Tensor, g: torch.Tensor, *, max_norm: Optional[float] = None,
                     lr: Optional[float] = None, ema: bool = True, zero_grad: bool = False,
-                    p_bf16: Optional[torch.Tensor] = None) -> None:
+                    p_bf16: Optional[torch.Tensor] = None, norm_sq: Optional[torch.Tensor] = None) -> None:
         """[clip ;] optimizer.step() ; EMA / slow-fast update
         (sfron.py:213-222,255-257; runners/diffusion.py:1156-1180; DiT/forget.py:310-322)."""
         self._step(p, g, mask=None, mask_order="mask_then_clip", max_norm=max_norm, ema=ema, lr=lr,
-                   zero_grad=zero_grad, p_bf16=p_bf16)
+                   zero_grad=zero_grad, p_bf16=p_bf16, norm_sq=norm_sq)
 
     def joint_step(self, p: torch.Tensor, g: torch.Tensor, *, mask: Optional[torch.Tensor] = None,
                    use_mask: bool = True, max_norm: Optional[float] = None, lr: Optional[float] = None,
