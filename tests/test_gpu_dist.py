@@ -187,9 +187,14 @@ def _peer_exchange(rank, world, dev):
             ref = O.FlatReferenceLoop({"w": (n,)}, {"w": theta0}, "adamw", dict(lr=1e-4), ema_mode="dit", ema_a=0.9999)
             ref.forget_step({"w": gbar_f}, mask={"w": ref_mask}, max_norm=1.0)
             ref.remain_step({"w": gbar_r}, ema=True)
-            tol = 1e-6 if (g_dtype == torch.float32 and (name == "p2p" or world == 2)) else 2e-5
-            # (multimem at world > 2 sums in the switch's order, and bf16 multimem returns a bf16-rounded mean:
-            #  where Adam normalises a near-cancelling gradient those last-bit differences are amplified)
+            # fp32 / P2P (and any transport at world 2) reproduces the oracle's rank-order sum exactly: 1e-6.  multimem at
+            # world > 2 sums in the switch's order (last-bit differences, amplified where Adam normalises a
+            # near-cancelling gradient): 2e-5.  bf16 over multimem comes back ROUNDED TO bf16 by the switch (2^-9
+            # relative on the gradient): the north star's bf16 bar, 1e-2.
+            if g_dtype == torch.bfloat16 and name == "multimem":
+                tol = 1e-2
+            else:
+                tol = 1e-6 if (g_dtype == torch.float32 and (name == "p2p" or world == 2)) else 2e-5
             full = w_sym.tensor[:n]
             assert _close(full, ref.flat("p"), tol), f"{name}/{g_dtype}: weights differ from the oracle"
             assert bool((w_sym.tensor[n:] == 7.0).all()), "padding was written"
