@@ -558,8 +558,8 @@ def run_dp(args, rank, world, dev):
                 "note": "same data-parallel step with torch.distributed reduce_scatter_tensor / all_gather_into_tensor "
                         "(NCCL) around the shard-local kernels"}
             del r
-            other = "p2p" if main_transport != "p2p" else ("multimem" if xchg.pad.has_multicast else None)
-            if other:
+            others = [t for t in ("p2p", "tma") + (("multimem",) if xchg.pad.has_multicast else ()) if t != main_transport]
+            for other in others:
                 r = measure(other, torch.float32, "f32", k, 3)
                 extra[f"{other}_transport"] = {"ms_per_step": round(r["ms_per_step"], 4),
                                                "value": round(BYTES_PER_ELEM * n / r["ms_per_step"] / 1e6, 1),

@@ -339,6 +339,11 @@ SFR_API int sfr_gather_segments(float* flat, const void* const* srcs_dev,
  *   SFR_XP_MULTIMEM  multimem.ld_reduce / multimem.st on the multicast address: the NVSwitch sums the
  *                    gradients (fp32 accumulation; bf16 results are rounded to bf16) and replicates the
  *                    weight stores
+ *   SFR_XP_TMA       the same mapped pointers and the same rank-order fp32 sum as SFR_XP_P2P, but the NVLink
+ *                    traffic is moved by TMA bulk copies (cp.async.bulk + mbarrier) through a shared-memory
+ *                    ring / staging buffers, off the load-store pipeline that streams the shard's local
+ *                    state — so HBM time and NVLink time overlap inside one kernel.  sfr_peer_fused_update
+ *                    uses it for both directions or not at all (g_transport == bc_transport)
  * `average` != 0 divides the sum by `world` (true division), the mean DataParallel's loss takes over
  * the global batch.
  *
@@ -349,6 +354,7 @@ SFR_API int sfr_gather_segments(float* flat, const void* const* srcs_dev,
 #define SFR_MAX_PEERS 8
 #define SFR_XP_P2P 1
 #define SFR_XP_MULTIMEM 2
+#define SFR_XP_TMA 3
 
 typedef struct sfr_peer_buf {
   void* ptrs[SFR_MAX_PEERS];

@@ -146,7 +146,7 @@ def _peer_exchange(rank, world, dev):
     sg = ShardGroup(n, padded_len=n_pad)
     xchg = PeerExchange(sg, dev, transport="auto", timeout_s=20.0)
     has_mc = xchg.pad.has_multicast
-    transports = ["p2p"] + (["multimem"] if has_mc else [])
+    transports = ["p2p", "tma"] + (["multimem"] if has_mc else [])
     ref_mask = O.flat_ratio_mask(ff, rf, 1.0)
     gbar_f, gbar_r = O.dp_reduce(gf), O.dp_reduce(gr)
     for g_dtype in (torch.float32, torch.bfloat16):
@@ -158,7 +158,7 @@ def _peer_exchange(rank, world, dev):
             gbar_r = O.dp_reduce([t.bfloat16() for t in gr])
         for name in transports:
             xchg._want = name
-            exact = g_dtype == torch.float32 and (name == "p2p" or world == 2)
+            exact = g_dtype == torch.float32 and (name in ("p2p", "tma") or world == 2)
             hp = ShardedHotPath(sg, dev, sfr.OptConfig(kind="adamw", lr=1e-4), ema_mode="dit", ema_a=0.9999)
             hp.attach_exchange(xchg)
             hp.set_buffer("mask", sg.local(ref_mask).to(dev).to(torch.uint8))
@@ -194,7 +194,7 @@ def _peer_exchange(rank, world, dev):
             if g_dtype == torch.bfloat16 and name == "multimem":
                 tol = 1e-2
             else:
-                tol = 1e-6 if (g_dtype == torch.float32 and (name == "p2p" or world == 2)) else 2e-5
+                tol = 1e-6 if (g_dtype == torch.float32 and (name in ("p2p", "tma") or world == 2)) else 2e-5
             full = w_sym.tensor[:n]
             assert _close(full, ref.flat("p"), tol), f"{name}/{g_dtype}: weights differ from the oracle"
             assert bool((w_sym.tensor[n:] == 7.0).all()), "padding was written"

@@ -72,10 +72,18 @@ class Emulated:
         return O.dp_reduce([h.float() for h in self.g_host], average)
 
 
+TRANSPORTS = ["p2p", "tma"]      # load/store threads | TMA bulk copies through shared memory: same sums, same order
+
+
+def xp(sfr, name):
+    return {"p2p": sfr.capi.XP_P2P, "tma": sfr.capi.XP_TMA}[name]
+
+
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 @pytest.mark.parametrize("n", [16 * 8 * 5, 4099, 1_000_003])
 @pytest.mark.parametrize("g_dtype", [torch.float32, torch.bfloat16])
-def test_peer_reduce_k1_norm_bit_exact(sfr, dev, world, n, g_dtype):
+@pytest.mark.parametrize("transport", TRANSPORTS)
+def test_peer_reduce_k1_norm_bit_exact(sfr, dev, world, n, g_dtype, transport):
     """reduce-scatter + K1 + clip norm in one kernel == oracle on the DataParallel-reduced gradient."""
     capi = sfr.capi
     em = Emulated(sfr, dev, n, world, g_dtype)
@@ -91,7 +99,7 @@ def test_peer_reduce_k1_norm_bit_exact(sfr, dev, world, n, g_dtype):
         red = torch.full((hi - lo,), float("nan"), device=dev)
         acc = torch.full((hi - lo,), 1e-7, device=dev)
         mask = em.mask_host[lo:hi].to(dev)
-        capi.peer_reduce(em.g_buf, g_dtype, em.geom(r), capi.XP_P2P, True, g_red=red, mask=mask, sumsq=sumsq,
+        capi.peer_reduce(em.g_buf, g_dtype, em.geom(r), xp(sfr, transport), True, g_red=red, mask=mask, sumsq=sumsq,
                          fisher=acc, fisher_divisor=7.0)
         got_red[lo:hi] = red.cpu()
         got_acc[lo:hi] = acc.cpu()
@@ -108,7 +116,8 @@ def test_peer_reduce_k1_norm_bit_exact(sfr, dev, world, n, g_dtype):
     ("sgd", dict(lr=0.01, momentum=0.9, weight_decay=5e-4), "slowfast", 0.9),
 ])
 @pytest.mark.parametrize("g_dtype", [torch.float32, torch.bfloat16])
-def test_peer_sharded_steps_match_oracle(sfr, dev, world, kind, kw, ema_mode, ema_a, g_dtype):
+@pytest.mark.parametrize("transport", TRANSPORTS)
+def test_peer_sharded_steps_match_oracle(sfr, dev, world, kind, kw, ema_mode, ema_a, g_dtype, transport):
     """forget step (mask, clip; gradient from the local reduced shard) then remain step + EMA (gradient
     reduced on the fly), weights pushed to every rank: == FlatReferenceLoop on the reduced gradients."""
     capi = sfr.capi
@@ -133,7 +142,7 @@ def test_peer_sharded_steps_match_oracle(sfr, dev, world, kind, kw, ema_mode, em
     for r in range(world):
         lo, hi = em.bounds[r]
         red = torch.empty(hi - lo, device=dev)
-        capi.peer_reduce(em.g_buf, g_dtype, em.geom(r), capi.XP_P2P, True, g_red=red, mask=hps[r].mask, sumsq=sumsq)
+        capi.peer_reduce(em.g_buf, g_dtype, em.geom(r), xp(sfr, transport), True, g_red=red, mask=hps[r].mask, sumsq=sumsq)
         reds.append(red)
     sgd = kind == "sgd"
     for r in range(world):
@@ -143,8 +152,8 @@ def test_peer_sharded_steps_match_oracle(sfr, dev, world, kind, kw, ema_mode, em
         hp.step_count = 1
         a = hp._args(flags, False, 1.0, None)
         capi.peer_fused_update(em.w[r][lo:hi], em.geom(r), a, g_red=reds[r], m=hp.m, v=None if sgd else hp.v,
-                               mask=hp.mask, bc_f32=em.w_buf, bc_bf16=em.w16_buf, clip_sumsq=sumsq,
-                               consts_scratch=hp._consts_dev)
+                               mask=hp.mask, bc_f32=em.w_buf, bc_bf16=em.w16_buf, bc_transport=xp(sfr, transport),
+                               clip_sumsq=sumsq, consts_scratch=hp._consts_dev)
     # ---- remain: gradient reduced inside the update kernel, EMA, push
     for r in range(world):
         lo, hi = em.bounds[r]
@@ -152,7 +161,8 @@ def test_peer_sharded_steps_match_oracle(sfr, dev, world, kind, kw, ema_mode, em
         hp.step_count = 2
         a = hp._args(0, True, None, None)
         capi.peer_fused_update(em.w[r][lo:hi], em.geom(r), a, g=em2.g_buf, g_dtype=g_dtype, m=hp.m,
-                               v=None if sgd else hp.v, ema=hp.slow, bc_f32=em.w_buf, bc_bf16=em.w16_buf)
+                               v=None if sgd else hp.v, ema=hp.slow, bc_f32=em.w_buf, bc_bf16=em.w16_buf,
+                               g_transport=xp(sfr, transport), bc_transport=xp(sfr, transport))
     torch.cuda.synchronize()
     want = ref.flat("p")
     for r in range(world):
@@ -164,7 +174,8 @@ def test_peer_sharded_steps_match_oracle(sfr, dev, world, kind, kw, ema_mode, em
 
 
 @pytest.mark.parametrize("world", [2, 4])
-def test_peer_unclipped_step_is_bit_identical_to_single_vector_kernel(sfr, dev, world):
+@pytest.mark.parametrize("transport", TRANSPORTS)
+def test_peer_unclipped_step_is_bit_identical_to_single_vector_kernel(sfr, dev, world, transport):
     capi = sfr.capi
     n = 300_013
     em = Emulated(sfr, dev, n, world, seed=9)
@@ -179,7 +190,8 @@ def test_peer_unclipped_step_is_bit_identical_to_single_vector_kernel(sfr, dev, 
         hp.init_slow(em.w[r][lo:hi])
         hp.step_count = 1
         capi.peer_fused_update(em.w[r][lo:hi], em.geom(r), hp._args(0, True, None, None), g=em.g_buf, m=hp.m, v=hp.v,
-                               ema=hp.slow, bc_f32=em.w_buf)
+                               ema=hp.slow, bc_f32=em.w_buf, g_transport=xp(sfr, transport),
+                               bc_transport=xp(sfr, transport))
         assert bits_equal(hp.slow.cpu(), one.slow[lo:hi].cpu())
     assert bits_equal(em.w[world - 1][:n].cpu(), p_one.cpu())
 
@@ -203,6 +215,11 @@ def test_peer_broadcast_and_argument_errors(sfr, dev):
                          g_red=torch.empty(16, device=dev))
     with pytest.raises(capi.SfrError):                    # nothing to produce
         capi.peer_reduce(em.g_buf, torch.float32, em.geom(0), capi.XP_P2P, True)
+    with pytest.raises(capi.SfrError):                    # one fused kernel = one transport for both directions
+        hp = sfr.HotPath(em.bounds[0][1], dev, sfr.OptConfig(kind="adamw", lr=1e-4))
+        hp.step_count = 1
+        capi.peer_fused_update(em.w[0][:em.bounds[0][1]], em.geom(0), hp._args(0, False, None, None), g=em.g_buf,
+                               m=hp.m, v=hp.v, bc_f32=em.w_buf, g_transport=capi.XP_TMA, bc_transport=capi.XP_P2P)
 
 
 def test_peer_barrier_world_one_sums_its_payload(sfr, dev):

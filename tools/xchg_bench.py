@@ -82,7 +82,7 @@ def main():
     hp.mask.copy_((torch.rand(sg.n_local, device=dev, generator=gen) < 0.5).to(torch.uint8))
     hp.mark_mask_ready()
     hp.enable_graph_replay()
-    transports = ["p2p"] + (["multimem", "p2p+multimem"] if w32.has_multicast else [])
+    transports = ["p2p", "tma"] + (["multimem", "p2p+multimem"] if w32.has_multicast else [])
 
     ms = timed(lambda: xchg.barrier(), iters=50)
     emit("barrier", "flags", "-", ms, 0, 0)

@@ -20,7 +20,7 @@ LIB_NAME = "libsfron_b200.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
 STAMP_PATH = os.path.join(HERE, ".libsfron_b200.stamp")
 
-SOURCES = ["api.cu", "fisher.cu", "mask.cu", "select.cu", "update.cu", "extras.cu", "peer.cu"]
+SOURCES = ["api.cu", "fisher.cu", "mask.cu", "select.cu", "update.cu", "extras.cu", "peer.cu", "peer_tma.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -42,7 +42,7 @@ def _nvcc() -> str:
 def _source_digest() -> str:
     h = hashlib.sha256()
     files = [os.path.join(CSRC, s) for s in SOURCES] + [
-        os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "update_core.cuh"), os.path.join(INCLUDE, "sfron_b200.h"), __file__]
+        os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "update_core.cuh"), os.path.join(CSRC, "peer_common.cuh"), os.path.join(INCLUDE, "sfron_b200.h"), __file__]
     for f in files:
         with open(f, "rb") as fh:
             h.update(fh.read())

@@ -27,7 +27,7 @@ SELECT_BINS0, SELECT_BINS1 = 32768, 65536
 SELECT_BINS_ALLOC = 65536 + 128         # u64 words of a bins buffer (histogram + the scan's partials / ticket)
 MAX_THRESHOLDS = 8
 MAX_PEERS = 8
-XP_P2P, XP_MULTIMEM = 1, 2
+XP_P2P, XP_MULTIMEM, XP_TMA = 1, 2, 3
 OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2
 EMA_NONE, EMA_DDPM, EMA_DIT, EMA_SLOWFAST = 0, 1, 2, 3
 F_MASK, F_MASK_AFTER_CLIP, F_ZERO_GRAD, F_SGD_FIRST_STEP, F_WRITE_BF16 = 1, 2, 4, 8, 16

@@ -412,13 +412,17 @@ class PeerExchange:
         torch.cuda.synchronize(self.device)
         dist.barrier(group=shards.group)                   # every rank's pad is zero before the first epoch
 
-    # transport = "<reduce>" or "<reduce>+<push>" with each of auto | p2p | multimem, e.g. "p2p+multimem":
-    # gradients pulled through the mapped pointers, weights pushed through the multicast address.
+    # transport = "<reduce>" or "<reduce>+<push>" with each of auto | p2p | tma | multimem, e.g. "p2p+multimem":
+    # gradients pulled through the mapped pointers, weights pushed through the multicast address.  "tma" moves
+    # both directions with TMA bulk copies through shared memory (csrc/peer_tma.cu) and cannot be mixed inside one
+    # fused kernel.
     def _pick(self, which: int) -> int:
         want = self._want.split("+")
         want = want[which] if len(want) > 1 else want[0]
         if want == "p2p":
             return capi.XP_P2P
+        if want == "tma":
+            return capi.XP_TMA
         data = self._buffers[1:] or self._buffers
         mc = all(b.has_multicast for b in data)
         if want == "multimem":
@@ -441,7 +445,7 @@ class PeerExchange:
 
     @property
     def transport_name(self) -> str:
-        names = {capi.XP_P2P: "p2p", capi.XP_MULTIMEM: "multimem"}
+        names = {capi.XP_P2P: "p2p", capi.XP_MULTIMEM: "multimem", capi.XP_TMA: "tma"}
         r, p = names[self.reduce_transport], names[self.push_transport]
         return r if r == p else f"{r}+{p}"
 
