@@ -237,6 +237,10 @@ SFR_API int sfr_masked_sumsq(const void* g, int g_dtype, const uint8_t* mask, in
 #define SFR_F_ZERO_GRAD 4u       /* write zeros back to g                               */
 #define SFR_F_SGD_FIRST_STEP 8u  /* momentum buffer does not exist yet: buf = g         */
 #define SFR_F_WRITE_BF16 16u     /* also write bf16(p) to p_bf16 (working copy)         */
+#define SFR_F_REUSE_CONSTS 32u   /* consts_scratch_dev already holds THIS optimizer step's scalars: an earlier
+                                    launch of the same step on another range of the vector prepared them (a shard
+                                    updated in several pieces, e.g. pipelined against the backward pass).  The step
+                                    counter is not advanced and the scalars are not recomputed. */
 
 typedef struct sfr_update_args {
   int32_t opt;       /* SFR_OPT_*  */
@@ -385,23 +389,26 @@ SFR_API int sfr_peer_barrier(const sfr_peer_buf* pad, int world, int rank, const
  *   fisher_acc[i] += gbar[i]**2 / fisher_divisor           (K1; same rounding sequence as sfr_fisher_accum)
  *   *sumsq        += sum_i (gbar[i] * mask[i])**2          (mask may be NULL; same as sfr_masked_sumsq)
  * mask / g_red / fisher_acc are LOCAL shard pointers (element 0 = vector element lo). */
+/* max_ctas (both calls below): upper bound on the CTAs of the launch, 0 = as many as the kernel wants.  A small
+ * bound (16-32) lets an exchange kernel run BESIDE other work — the backward pass on another stream — instead of
+ * taking every SM; the TMA transport keeps NVLink busy from few CTAs. */
 SFR_API int sfr_peer_reduce(const sfr_peer_buf* g, int g_dtype, const sfr_peer_geom* geom, int transport,
                     int average, float* g_red, const uint8_t* mask, double* sumsq,
-                    float* fisher_acc, float fisher_divisor, sfr_stream_t stream);
+                    float* fisher_acc, float fisher_divisor, int max_ctas, sfr_stream_t stream);
 
 /* K3 on this rank's shard with the exchange on both sides.  Gradient source: `g_red` (local fp32 shard
  * left by sfr_peer_reduce — the clipped steps, whose norm must be known first) or, when g != NULL, the
  * peers' full gradients reduced on the fly (g_transport, average).  p / m / v / mask / ema are local
  * shard pointers.  Every updated weight is also pushed into all ranks' full-vector buffers: bc_f32
  * (fp32 weights; NULL = none) and/or bc_bf16 (bf16 working copy; NULL = none) via bc_transport.
- * args->flags: SFR_F_MASK | SFR_F_MASK_AFTER_CLIP | SFR_F_SGD_FIRST_STEP only.  Everything else as
+ * args->flags: SFR_F_MASK | SFR_F_MASK_AFTER_CLIP | SFR_F_SGD_FIRST_STEP | SFR_F_REUSE_CONSTS only.  Everything else as
  * sfr_fused_update (same arithmetic: the two share their per-element code). */
 SFR_API int sfr_peer_fused_update(float* p, const float* g_red, const sfr_peer_buf* g, int g_dtype,
                     int g_transport, int average, float* m, float* v, const uint8_t* mask,
                     float* ema, const sfr_peer_buf* bc_f32, const sfr_peer_buf* bc_bf16,
                     int bc_transport, const sfr_peer_geom* geom, const sfr_update_args* args,
                     const double* clip_sumsq, long long* step_counter_dev,
-                    void* consts_scratch_dev, sfr_stream_t stream);
+                    void* consts_scratch_dev, int max_ctas, sfr_stream_t stream);
 
 /* All-gather alone: push this rank's shard (src_local, n_local elements of elem_bytes = 2 | 4) into every
  * rank's full-vector buffer `dst` at element offset lo. */

@@ -30,7 +30,7 @@ MAX_PEERS = 8
 XP_P2P, XP_MULTIMEM, XP_TMA = 1, 2, 3
 OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2
 EMA_NONE, EMA_DDPM, EMA_DIT, EMA_SLOWFAST = 0, 1, 2, 3
-F_MASK, F_MASK_AFTER_CLIP, F_ZERO_GRAD, F_SGD_FIRST_STEP, F_WRITE_BF16 = 1, 2, 4, 8, 16
+F_MASK, F_MASK_AFTER_CLIP, F_ZERO_GRAD, F_SGD_FIRST_STEP, F_WRITE_BF16, F_REUSE_CONSTS = 1, 2, 4, 8, 16, 32
 
 EXPORTED_SYMBOLS = (
     "sfr_abi_version", "sfr_error_string", "sfr_device_info", "sfr_fisher_accum", "sfr_grad_accum",
@@ -147,11 +147,11 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.sfr_peer_barrier.argtypes = [C.POINTER(PeerBuf), C.c_int, C.c_int, vp, vp, C.c_int, C.c_uint64, vp]
     lib.sfr_peer_reduce.restype = C.c_int
     lib.sfr_peer_reduce.argtypes = [C.POINTER(PeerBuf), C.c_int, C.POINTER(PeerGeom), C.c_int, C.c_int, vp, vp, vp,
-                                    vp, f32, vp]
+                                    vp, f32, C.c_int, vp]
     lib.sfr_peer_fused_update.restype = C.c_int
     lib.sfr_peer_fused_update.argtypes = [vp, vp, C.POINTER(PeerBuf), C.c_int, C.c_int, C.c_int, vp, vp, vp, vp,
                                           C.POINTER(PeerBuf), C.POINTER(PeerBuf), C.c_int, C.POINTER(PeerGeom),
-                                          C.POINTER(UpdateArgs), vp, vp, vp, vp]
+                                          C.POINTER(UpdateArgs), vp, vp, vp, C.c_int, vp]
     lib.sfr_peer_broadcast.restype = C.c_int
     lib.sfr_peer_broadcast.argtypes = [vp, C.POINTER(PeerBuf), C.c_int, C.POINTER(PeerGeom), C.c_int, vp]
     if lib.sfr_abi_version() != ABI_VERSION:
@@ -449,7 +449,7 @@ def peer_barrier(pad: PeerBuf, world: int, rank: int, vals: Optional[torch.Tenso
 def peer_reduce(g: PeerBuf, g_dtype: torch.dtype, geom: PeerGeom, transport: int, average: bool, *,
                 g_red: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
                 sumsq: Optional[torch.Tensor] = None, fisher: Optional[torch.Tensor] = None,
-                fisher_divisor: float = 1.0) -> None:
+                fisher_divisor: float = 1.0, max_ctas: int = 0) -> None:
     for name, t in (("g_red", g_red), ("mask", mask), ("fisher", fisher)):
         if t is not None and t.numel() != geom.n_local:
             raise SfrError(ERR_ARG, "peer_reduce", f"{name} has {t.numel()} elements, the shard has {geom.n_local}")
@@ -459,7 +459,7 @@ def peer_reduce(g: PeerBuf, g_dtype: torch.dtype, geom: PeerGeom, transport: int
     _check(load().sfr_peer_reduce(C.byref(g), gd, C.byref(geom), transport, int(bool(average)),
                                   _ptr(g_red, torch.float32, "g_red"), _ptr(mask, _MASK_DTYPES, "mask"),
                                   _ptr(sumsq, torch.float64, "sumsq"), _ptr(fisher, torch.float32, "fisher"),
-                                  float(fisher_divisor), _stream()), "sfr_peer_reduce")
+                                  float(fisher_divisor), int(max_ctas), _stream()), "sfr_peer_reduce")
 
 
 def peer_fused_update(p: torch.Tensor, geom: PeerGeom, args: UpdateArgs, *, g_red: Optional[torch.Tensor] = None,
@@ -469,7 +469,7 @@ def peer_fused_update(p: torch.Tensor, geom: PeerGeom, args: UpdateArgs, *, g_re
                       bc_f32: Optional[PeerBuf] = None, bc_bf16: Optional[PeerBuf] = None,
                       bc_transport: int = XP_P2P, clip_sumsq: Optional[torch.Tensor] = None,
                       step_counter: Optional[torch.Tensor] = None,
-                      consts_scratch: Optional[torch.Tensor] = None) -> None:
+                      consts_scratch: Optional[torch.Tensor] = None, max_ctas: int = 0) -> None:
     n = geom.n_local
     for name, t in (("p", p), ("g_red", g_red), ("m", m), ("v", v), ("mask", mask), ("ema", ema)):
         if t is not None and t.numel() != n:
@@ -485,7 +485,7 @@ def peer_fused_update(p: torch.Tensor, geom: PeerGeom, args: UpdateArgs, *, g_re
         C.byref(bc_f32) if bc_f32 is not None else None, C.byref(bc_bf16) if bc_bf16 is not None else None,
         bc_transport, C.byref(geom), C.byref(args), _ptr(clip_sumsq, torch.float64, "clip_sumsq"),
         _ptr(step_counter, torch.int64, "step_counter"), _ptr(consts_scratch, torch.uint8, "consts_scratch"),
-        _stream()), "sfr_peer_fused_update")
+        int(max_ctas), _stream()), "sfr_peer_fused_update")
 
 
 def peer_broadcast(src: torch.Tensor, dst: PeerBuf, geom: PeerGeom, transport: int) -> None:

@@ -437,7 +437,7 @@ extern "C" int sfr_peer_barrier(const sfr_peer_buf* pad, int world, int rank, co
 
 extern "C" int sfr_peer_reduce(const sfr_peer_buf* g, int g_dtype, const sfr_peer_geom* geom, int transport,
                                int average, float* g_red, const uint8_t* mask, double* sumsq,
-                               float* fisher_acc, float fisher_divisor, sfr_stream_t stream) {
+                               float* fisher_acc, float fisher_divisor, int max_ctas, sfr_stream_t stream) {
   using namespace sfr;
   SFR_REQUIRE_PTR(g);
   if (!geom_ok(geom)) return SFR_ERR_ARG;
@@ -453,7 +453,9 @@ extern "C" int sfr_peer_reduce(const sfr_peer_buf* g, int g_dtype, const sfr_pee
   if (rc != SFR_OK) return rc;
   SFR_ENTER_DEVICE(g->ptrs[geom->rank]);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (gs == GS_TMA) return launch_reduce_tma(g_dtype, src, geom, g_red, mask, sumsq, fisher_acc, fisher_divisor, s);
+  if (max_ctas < 0) return SFR_ERR_ARG;
+  if (gs == GS_TMA)
+    return launch_reduce_tma(g_dtype, src, geom, g_red, mask, sumsq, fisher_acc, fisher_divisor, max_ctas, s);
   if (gs == GS_P2P) {
     if (g_dtype == SFR_F32) launch_reduce<SFR_F32, GS_P2P>(s, src, geom, g_red, mask, sumsq, fisher_acc, fisher_divisor);
     else launch_reduce<SFR_BF16, GS_P2P>(s, src, geom, g_red, mask, sumsq, fisher_acc, fisher_divisor);
@@ -470,15 +472,15 @@ extern "C" int sfr_peer_fused_update(float* p, const float* g_red, const sfr_pee
                                      const sfr_peer_buf* bc_bf16, int bc_transport,
                                      const sfr_peer_geom* geom, const sfr_update_args* a,
                                      const double* clip_sumsq, long long* step_counter,
-                                     void* consts_scratch, sfr_stream_t stream) {
+                                     void* consts_scratch, int max_ctas, sfr_stream_t stream) {
   using namespace sfr;
   SFR_REQUIRE_PTR(a);
-  if (!geom_ok(geom)) return SFR_ERR_ARG;
+  if (!geom_ok(geom) || max_ctas < 0) return SFR_ERR_ARG;
   if (a->opt < SFR_OPT_SGD || a->opt > SFR_OPT_ADAMW) return SFR_ERR_ARG;
   if (a->ema_mode < SFR_EMA_NONE || a->ema_mode > SFR_EMA_SLOWFAST) return SFR_ERR_ARG;
   if (g != nullptr && g_dtype != SFR_F32 && g_dtype != SFR_BF16) return SFR_ERR_ARG;
   // the gradient belongs to the peers while they read it, and the working copy travels through bc_bf16
-  const uint32_t known = SFR_F_MASK | SFR_F_MASK_AFTER_CLIP | SFR_F_SGD_FIRST_STEP;
+  const uint32_t known = SFR_F_MASK | SFR_F_MASK_AFTER_CLIP | SFR_F_SGD_FIRST_STEP | SFR_F_REUSE_CONSTS;
   if (a->flags & ~known) return SFR_ERR_ARG;
   if ((a->flags & SFR_F_MASK) && (a->flags & SFR_F_MASK_AFTER_CLIP)) return SFR_ERR_ARG;
   if (a->opt != SFR_OPT_SGD && a->step < 1 && step_counter == nullptr) return SFR_ERR_ARG;
@@ -510,10 +512,12 @@ extern "C" int sfr_peer_fused_update(float* p, const float* g_red, const sfr_pee
   const DevConsts* c_dev = nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if ((a->lr_table_dev == nullptr) != (a->lr_index_dev == nullptr)) return SFR_ERR_NULL;
-  if (step_counter != nullptr || a->lr_table_dev != nullptr) SFR_REQUIRE_PTR(consts_scratch);
+  if (step_counter != nullptr || a->lr_table_dev != nullptr || (a->flags & SFR_F_REUSE_CONSTS))
+    SFR_REQUIRE_PTR(consts_scratch);
   if (consts_scratch != nullptr) {
     if (!aligned16(consts_scratch)) return SFR_ERR_ALIGN;
-    launch_update_consts(*a, has_momentum, step_counter, clip_sumsq, consts_scratch, s);
+    if (!(a->flags & SFR_F_REUSE_CONSTS))
+      launch_update_consts(*a, has_momentum, step_counter, clip_sumsq, consts_scratch, s);
     c_dev = reinterpret_cast<const DevConsts*>(consts_scratch);
   }
   const int64_t nvec = geom->n_local >> 2;
@@ -523,7 +527,7 @@ extern "C" int sfr_peer_fused_update(float* p, const float* g_red, const sfr_pee
     // one kernel moves both directions through the copy engine: no mixing with the load/store transports
     if ((gs != GS_TMA && gs != GS_LOCAL) || (pushes && bc_transport != SFR_XP_TMA)) return SFR_ERR_ARG;
     return launch_update_tma(a->opt, a->ema_mode, gt, gs == GS_TMA, p, src, m, v, mask, ema, bc32, bc16, geom, c, c_dev,
-                             clip_sumsq, s);
+                             clip_sumsq, max_ctas, s);
   }
   switch (a->opt) {
     case SFR_OPT_SGD:

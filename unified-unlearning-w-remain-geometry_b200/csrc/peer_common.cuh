@@ -204,9 +204,10 @@ __device__ __forceinline__ void push_bf16x1(const Sink& k, int64_t gi, float v) 
 
 // ---- entry points of peer_tma.cu (SFR_XP_TMA) ---------------------------------------------------------------
 int launch_reduce_tma(int g_dtype, const GradSrc& src, const sfr_peer_geom* q, float* g_red, const uint8_t* mask,
-                      double* sumsq, float* fisher, float fisher_div, cudaStream_t s);
+                      double* sumsq, float* fisher, float fisher_div, int max_ctas, cudaStream_t s);
 int launch_update_tma(int opt, int ema_mode, int gt, bool from_peers, float* p, const GradSrc& src, float* m, float* v,
                       const uint8_t* mask, float* ema, const Sink& bc32, const Sink& bc16, const sfr_peer_geom* q,
-                      const UpdateConsts& c, const DevConsts* c_dev, const double* clip_sumsq, cudaStream_t s);
+                      const UpdateConsts& c, const DevConsts* c_dev, const double* clip_sumsq, int max_ctas,
+                      cudaStream_t s);
 
 }  // namespace sfr

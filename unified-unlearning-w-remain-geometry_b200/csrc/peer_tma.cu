@@ -416,11 +416,12 @@ cudaError_t launch_update_tma_ema(int ema_mode, int gt, bool from_peers, int gri
 }  // namespace
 
 int launch_reduce_tma(int g_dtype, const GradSrc& src, const sfr_peer_geom* q, float* g_red, const uint8_t* mask,
-                      double* sumsq, float* fisher, float fisher_div, cudaStream_t s) {
+                      double* sumsq, float* fisher, float fisher_div, int max_ctas, cudaStream_t s) {
   const int tile_bytes = kTileElems * (g_dtype == SFR_F32 ? 4 : 2);
   const TmaGeom geo = ring_geometry(q->world, tile_bytes, 0);
   const int64_t ntiles = (q->n_local + kTileElems - 1) / kTileElems;
-  const int grid = persistent_grid(ntiles, geo.ctas_per_sm);
+  int grid = persistent_grid(ntiles, geo.ctas_per_sm);
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   cudaError_t e;
   if (g_dtype == SFR_F32) {
     e = opt_in_smem(peer_reduce_tma_kernel<SFR_F32>, geo.smem);
@@ -439,12 +440,14 @@ int launch_reduce_tma(int g_dtype, const GradSrc& src, const sfr_peer_geom* q, f
 
 int launch_update_tma(int opt, int ema_mode, int gt, bool from_peers, float* p, const GradSrc& src, float* m, float* v,
                       const uint8_t* mask, float* ema, const Sink& bc32, const Sink& bc16, const sfr_peer_geom* q,
-                      const UpdateConsts& c, const DevConsts* c_dev, const double* clip_sumsq, cudaStream_t s) {
+                      const UpdateConsts& c, const DevConsts* c_dev, const double* clip_sumsq, int max_ctas,
+                      cudaStream_t s) {
   const int fixed = 2 * kTileElems * 4 + 2 * kTileElems * 2;   // the two staging rings
   const int tile_bytes = kTileElems * (gt == SFR_F32 ? 4 : 2);
   TmaGeom geo = from_peers ? ring_geometry(q->world, tile_bytes, fixed) : TmaGeom{1, 2, fixed};
   const int64_t ntiles = (q->n_local + kTileElems - 1) / kTileElems;
-  const int grid = persistent_grid(ntiles, geo.ctas_per_sm);
+  int grid = persistent_grid(ntiles, geo.ctas_per_sm);
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   cudaError_t e;
   switch (opt) {
     case SFR_OPT_SGD:

@@ -415,7 +415,7 @@ extern "C" int sfr_fused_update(float* p, void* g, float* m, float* v, const uin
   if (a->ema_mode < SFR_EMA_NONE || a->ema_mode > SFR_EMA_SLOWFAST) return SFR_ERR_ARG;
   if (a->g_dtype != SFR_F32 && a->g_dtype != SFR_BF16) return SFR_ERR_ARG;
   const uint32_t known = SFR_F_MASK | SFR_F_MASK_AFTER_CLIP | SFR_F_ZERO_GRAD |
-                         SFR_F_SGD_FIRST_STEP | SFR_F_WRITE_BF16;
+                         SFR_F_SGD_FIRST_STEP | SFR_F_WRITE_BF16 | SFR_F_REUSE_CONSTS;
   if (a->flags & ~known) return SFR_ERR_ARG;
   if ((a->flags & SFR_F_MASK) && (a->flags & SFR_F_MASK_AFTER_CLIP)) return SFR_ERR_ARG;
   if (a->opt != SFR_OPT_SGD && a->step < 1 && step_counter == nullptr) return SFR_ERR_ARG;
@@ -443,12 +443,14 @@ extern "C" int sfr_fused_update(float* p, void* g, float* m, float* v, const uin
   const DevConsts* c_dev = nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if ((a->lr_table_dev == nullptr) != (a->lr_index_dev == nullptr)) return SFR_ERR_NULL;
-  if (step_counter != nullptr || a->lr_table_dev != nullptr) SFR_REQUIRE_PTR(consts_scratch);
+  if (step_counter != nullptr || a->lr_table_dev != nullptr || (a->flags & SFR_F_REUSE_CONSTS))
+    SFR_REQUIRE_PTR(consts_scratch);
   if (consts_scratch != nullptr) {
     // one-thread prep kernel: step-dependent scalars (from the device counter if given: graph
     // replay) and the clip coefficient, precomputed so the main kernel never stalls on them
     if (!aligned16(consts_scratch)) return SFR_ERR_ALIGN;
-    launch_update_consts(*a, has_momentum, step_counter, clip_sumsq, consts_scratch, s);
+    if (!(a->flags & SFR_F_REUSE_CONSTS))
+      launch_update_consts(*a, has_momentum, step_counter, clip_sumsq, consts_scratch, s);
     c_dev = reinterpret_cast<const DevConsts*>(consts_scratch);
   }
 
