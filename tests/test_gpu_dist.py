@@ -213,8 +213,9 @@ def _peer_exchange(rank, world, dev):
             # is itself ~1e-5 off the exact norm (measured below; ours accumulates in double), and the square doubles it
             exact = gb.double().pow(2).sum().sqrt().item()
             norm_err = abs(float(O.clip_grad_norm([gb.clone()], 1e30)) - exact) / exact
+            # (bf16 over multimem: the switch returns the MEAN rounded to bf16, 2^-9 relative, and the Fisher squares it)
             assert _close(hp.remain_fisher, sg.local(acc["w"]),
-                          1e-2 if g_dtype == torch.bfloat16 else 1e-6 + 2.5 * norm_err), \
+                          (4e-2 if name == "multimem" else 1e-2) if g_dtype == torch.bfloat16 else 1e-6 + 2.5 * norm_err), \
                 f"{name}/{g_dtype}: clipped Fisher, max rel err " \
                 f"{((hp.remain_fisher.cpu() - sg.local(acc['w'])).abs() / sg.local(acc['w']).abs().clamp_min(1e-30)).max()}"
     # ---- the barrier's payload: sum over ranks in rank order, identical bits everywhere
@@ -248,6 +249,104 @@ def _bucketed_reducer(rank, world, dev):
     assert torch.equal(shard, mono), "bucketed exchange != monolithic all-reduce"
 
 
+def _overlapped_backward(rank, world, dev):
+    """ShardGroup(parts=2) + OverlappedBackward: the late half of the flat vector is exchanged on a side stream from
+    INSIDE loss.backward() (reduce + norm for the clipped forget step; reduce + Adam + EMA + weight push for the remain
+    step), the early half after it.  Weights on every rank == the oracle on the rank-order mean of the recorded
+    gradients; also replayed from a CUDA graph."""
+    import torch.distributed as dist
+    import torch.nn as nn
+    import sfron_b200 as sfr
+    from sfron_b200.dist import OverlappedBackward, PeerExchange, ShardGroup, ShardedHotPath
+    from oracle import sfron_oracle as O
+    for graphed in (False, True):
+        torch.manual_seed(0)                                # identical weights on every rank
+        model = nn.Sequential(nn.Linear(48, 160), nn.Tanh(), nn.Linear(160, 160), nn.Tanh(), nn.Linear(160, 24)).to(dev)
+        n = sum(p.numel() for p in model.parameters())
+        n_pad = -(-n // (32 * world)) * (32 * world)
+        sg = ShardGroup(n, padded_len=n_pad, parts=2)
+        xchg = PeerExchange(sg, dev, transport="tma", timeout_s=20.0)
+        sym = {}
+
+        def alloc(role, numel, dtype):
+            sym[role] = xchg.alloc(numel, dtype)
+            return sym[role].tensor
+
+        flat = sfr.FlatParams(model, dev, pad_multiple=32 * world, alloc=alloc)
+        theta0 = flat.p.detach().cpu().clone()
+        hp = ShardedHotPath(sg, dev, sfr.OptConfig(kind="adam", lr=1e-3), ema_mode="ddpm", ema_a=1e-2)
+        hp.attach_exchange(xchg)
+        ov = OverlappedBackward(flat, sg, xchg.sibling(), max_ctas=4)
+        assert 0 < ov._need < len(flat._train_params)
+        mask = torch.rand(n, generator=torch.Generator().manual_seed(5)) < 0.5
+        hp.set_buffer("mask", sg.local(mask.to(torch.uint8)).to(dev))
+        p_views = [flat.p[g:g + c] for g, _, c in sg.spans]
+        hp.init_slow(sg.local(flat.p))
+        if graphed:
+            hp.enable_graph_replay()
+        xs = [torch.randn(16, 48, generator=torch.Generator().manual_seed(100 * it + rank)).to(dev) for it in range(4)]
+        x_static = torch.zeros(16, 48, device=dev)
+        recorded = []
+
+        def body():
+            for kind in ("forget", "remain"):
+                loss = model(x_static).pow(2).mean() * (3.0 if kind == "forget" else 1.0)
+                if kind == "forget":
+                    hp.dp_begin_step(ov, p_views, sym["g"], weights=sym["p"], mask=hp.require_mask(), max_norm=0.05)
+                else:
+                    hp.dp_begin_step(ov, p_views, sym["g"], weights=sym["p"], ema=True)
+                loss.backward()
+                if not graphed:
+                    recorded.append(flat.g.detach().cpu().clone())
+                hp.dp_finish_step()
+                flat.g.zero_()
+
+        flat.g.zero_()
+        if graphed:
+            side = torch.cuda.Stream()
+            graph = torch.cuda.CUDAGraph()
+            x_static.copy_(xs[0])
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body()                                      # eager iteration 0 (also the warm-up)
+            torch.cuda.current_stream().wait_stream(side)
+            with torch.cuda.graph(graph):
+                body()
+            for x in xs[1:]:
+                x_static.copy_(x)
+                graph.replay()
+        else:
+            for x in xs:
+                x_static.copy_(x)
+                body()
+        torch.cuda.synchronize()
+        xchg.check()
+        ov.xchg.check()
+        gathered = [torch.empty_like(flat.p_padded) for _ in range(world)]
+        dist.all_gather(gathered, flat.p_padded)
+        assert all(torch.equal(t, gathered[0]) for t in gathered), "ranks hold different weights"
+        if not graphed:
+            # the oracle needs every rank's gradient of every pass
+            mine = torch.stack(recorded).to(dev)
+            every = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            ref = O.FlatReferenceLoop({"w": (n,)}, {"w": theta0}, "adam", dict(lr=1e-3), ema_mode="ddpm", ema_a=1e-2)
+            for i in range(0, len(recorded), 2):
+                ref.forget_step({"w": O.dp_reduce([e[i].cpu() for e in every])}, mask={"w": mask}, max_norm=0.05)
+                ref.remain_step({"w": O.dp_reduce([e[i + 1].cpu() for e in every])}, ema=True)
+            want_p, want_slow = ref.flat("p"), ref.flat("slow")
+            assert _close(flat.p, want_p), "overlapped data-parallel steps differ from the oracle"
+            assert _close(hp.slow, sg.local(want_slow))
+            eager_final = flat.p.detach().cpu().clone()
+            dist.barrier()
+            torch.save(eager_final, f"/tmp/_sfr_ov_{rank}.pt")
+        else:
+            # same data, same kernels, replayed: the weights of the eager run
+            assert _close(flat.p, torch.load(f"/tmp/_sfr_ov_{rank}.pt"), 1e-6)
+            assert int(hp.step_dev) == 8
+        ov.remove()
+
+
 # ------------------------------------------------------------------------------------------------
 def test_sharded_masks_bit_exact_over_nccl():
     _spawn("_sharded_masks")
@@ -263,3 +362,7 @@ def test_fused_peer_exchange_p2p_and_multimem():
 
 def test_bucketed_gradient_reducer_over_nccl():
     _spawn("_bucketed_reducer")
+
+
+def test_exchange_overlapped_with_backward():
+    _spawn("_overlapped_backward")

@@ -113,15 +113,17 @@ def run_ours(args, dev, ac, rank, world):
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     opt = sfr.OptConfig(kind="adamw", lr=1e-4, weight_decay=0.0)
     peer = world > 1 and args.dp_exchange.startswith("peer")
-    xchg, sym = None, {}
+    overlap = peer and args.dp_exchange.startswith("peer-overlap")
+    xchg, sym, ov = None, {}, None
     if peer:
         # gradients and the weights the model reads live in symmetric (peer-mapped) memory: the data-parallel
         # kernels pull gradient shards out of every rank's buffer and push updated weights into every rank's
         import torch.distributed as dist
         from sfron_b200.dist import PeerExchange, ShardGroup, ShardedHotPath
         n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
-        n_pad = -(-n_train // (16 * world)) * (16 * world)
-        sg = ShardGroup(n_train, padded_len=n_pad)
+        parts = 2 if overlap else 1
+        n_pad = -(-n_train // (16 * world * parts)) * (16 * world * parts)
+        sg = ShardGroup(n_train, padded_len=n_pad, parts=parts)
         xchg = PeerExchange(sg, dev, transport=args.dp_exchange.partition(":")[2] or "auto")
 
         def alloc(role, numel, dtype):
@@ -130,11 +132,15 @@ def run_ours(args, dev, ac, rank, world):
             sym[role] = xchg.alloc(numel, dtype)
             return sym[role].tensor
 
-        flat = sfr.FlatParams(model, dev, pad_multiple=16 * world, alloc=alloc)
+        flat = sfr.FlatParams(model, dev, pad_multiple=16 * world * parts, alloc=alloc)
         assert flat.n == n_train and flat.n_padded == n_pad
         hp = ShardedHotPath(sg, dev, opt, ema_mode="dit", ema_a=0.9999)
         hp.attach_exchange(xchg)
-        lo, hi = sg.lo, sg.hi
+        lo, hi = (sg.lo, sg.hi) if not overlap else (0, sg.n_local)
+        if overlap:
+            # the late half of the vector is exchanged on a side stream, by a few CTAs, while backward still runs
+            from sfron_b200.dist import OverlappedBackward
+            ov = OverlappedBackward(flat, sg, xchg.sibling(), max_ctas=args.overlap_ctas)
     else:
         flat = sfr.FlatParams(model, dev, pad_multiple=16 * world)
     if peer:
@@ -149,10 +155,15 @@ def run_ours(args, dev, ac, rank, world):
         sg = None
         hp = sfr.HotPath(flat.n, dev, opt, ema_mode="dit", ema_a=0.9999)
         lo, hi = 0, flat.n
-    p_loc = flat.p[lo:hi]
-    w_loc = None if flat.p_work is None else flat.p_work[lo:hi]
+    if overlap:
+        # two spans per rank: the fp32 master shard is their concatenation (bf16 model) or two views of the weights
+        p_loc = sg.local(flat.p) if flat.p_work is not None else [flat.p[g:g + c] for g, _, c in sg.spans]
+        w_loc = None
+    else:
+        p_loc = flat.p[lo:hi]
+        w_loc = None if flat.p_work is None else flat.p_work[lo:hi]
     weights_full = flat.p_padded if flat.p_work is None else flat.p_work_padded   # what the model reads
-    hp.init_slow(p_loc)
+    hp.init_slow(sg.local(flat.p) if overlap else p_loc)
     frozen_slow = flat.frozen.clone()
     hp.mask.copy_((torch.rand(hi - lo, device=dev, generator=gen) < 0.5).to(torch.uint8))
     hp.mark_mask_ready()
@@ -183,6 +194,28 @@ def run_ours(args, dev, ac, rank, world):
     ac = ac.to(dt)
 
     def forget_body(x, t, noise, y_f, y_r):
+        if overlap:
+            side = ov.side
+            main = torch.cuda.current_stream()
+            kw = dict(weights=sym.get("p"), weights_bf16=sym.get("p_work"))
+            loss = args.forget_alpha * -synthetic_loss(model, x, t, y_f, noise, ac)
+            hp.dp_begin_step(ov, p_loc, sym["g"], mask=hp.require_mask(), max_norm=1.0, **kw)
+            loss.backward()                              # late half: reduce + norm on the side stream meanwhile
+            hp.dp_finish_step()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                flat.g.zero_()                           # the gradient memset runs beside the remain forward
+            loss = synthetic_loss(model, x, t, y_r, noise, ac)
+            main.wait_stream(side)
+            hp.dp_begin_step(ov, p_loc, sym["g"], ema=True, **kw)
+            loss.backward()                              # late half: reduce + K3 + EMA + push on the side stream
+            hp.dp_finish_step()
+            hp.ema_only(flat.frozen, frozen_slow)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                flat.g.zero_()
+            main.wait_stream(side)
+            return
         (args.forget_alpha * -synthetic_loss(model, x, t, y_f, noise, ac)).backward()
         if peer:
             # barrier -> reduce + masked norm (one kernel over NVLink) -> barrier carrying the norm -> K3 + weight
@@ -301,10 +334,13 @@ def main():
                     help="ours arm: capture the whole forget iteration (collectives included) in a CUDA graph and replay it")
     ap.add_argument("--dp-exchange", default="peer",
                     help="peer[:transport] (default): the library's fused exchange kernels over NVLink peer memory "
-                         "(transport auto | p2p | multimem | <reduce>+<push>); reduce_scatter | allreduce: NCCL collectives "
+                         "(transport auto | tma | p2p | multimem | <reduce>+<push>); peer-overlap[:transport]: the same, with "
+                         "the late half of the vector exchanged beside the backward pass; reduce_scatter | allreduce: NCCL collectives "
                          "around the shard-local kernels; bucketed: NCCL all-reduce in buckets started from autograd "
                          "hooks while backward still runs (sfron_b200.dist.BucketedGradReducer)")
     ap.add_argument("--bucket-mb", type=int, default=64)
+    ap.add_argument("--overlap-ctas", type=int, default=32,
+                    help="peer-overlap[:transport]: CTAs of the exchange kernels that run beside the backward pass")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -63,9 +63,15 @@ class ShardGroup:
     padded_len: length of the (padded) flat buffers, a multiple of world x align.  When given, shard r
     is the r-th EQUAL slice of the padded buffer clipped to [0, n_total): reduce-scatter and all-gather
     then work in place on equal chunks, while kernels only ever see the valid elements.
+
+    parts > 1 (needs padded_len, a multiple of world x align x parts): the vector is cut into `parts` equal
+    consecutive pieces and EVERY piece is split over the ranks, so a rank owns `parts` spans — its local buffers
+    are their concatenation.  The late pieces of a model's flat vector receive their gradients first during
+    backward, so their exchange can run while backward is still producing the early ones (OverlappedBackward).
+    `spans` = [(first global element, offset in the local buffers, elements)], one per part.
     """
 
-    def __init__(self, n_total: int, group=None, align: int = 16, padded_len: Optional[int] = None):
+    def __init__(self, n_total: int, group=None, align: int = 16, padded_len: Optional[int] = None, parts: int = 1):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.group = group
@@ -83,6 +89,22 @@ class ShardGroup:
             self.bounds = [(min(r * self.per, self.n_total), min((r + 1) * self.per, self.n_total))
                            for r in range(self.world)]
         self.lo, self.hi = self.bounds[self.rank]
+        self.parts = int(parts)
+        if self.parts == 1:
+            self.spans = [(self.lo, 0, self.hi - self.lo)]
+        else:
+            if padded_len is None or padded_len % (self.world * align * self.parts):
+                raise ValueError("parts > 1 needs padded_len, a multiple of world * align * parts")
+            piece = padded_len // self.parts
+            per = piece // self.world
+            self.spans, off = [], 0
+            for k in range(self.parts):
+                glo = min(k * piece + self.rank * per, self.n_total)
+                ghi = min(k * piece + (self.rank + 1) * per, self.n_total)
+                self.spans.append((glo, off, ghi - glo))
+                off += ghi - glo
+            self.lo = self.hi = None               # no single contiguous shard: the NCCL helpers do not apply
+            self.per = None
         self._nccl = dist.get_backend(group) == "nccl"
 
     @staticmethod
@@ -91,10 +113,13 @@ class ShardGroup:
 
     @property
     def n_local(self) -> int:
-        return self.hi - self.lo
+        return sum(c for _, _, c in self.spans)
 
     def local(self, flat: torch.Tensor) -> torch.Tensor:
-        return flat[self.lo:self.hi]
+        """This rank's elements of a full vector: a view for one span, the concatenation of the spans otherwise."""
+        if self.parts == 1:
+            return flat[self.lo:self.hi]
+        return torch.cat([flat[g:g + c] for g, _, c in self.spans])
 
     def all_reduce_(self, t: torch.Tensor) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
@@ -224,6 +249,8 @@ class ShardedHotPath(HotPath):
         self.select_graphs = False                 # the select's cross-rank reductions are torch.distributed calls
         self.xchg: Optional["PeerExchange"] = None
         self._g_red: dict = {}
+        self._pending: Optional[dict] = None
+        self._sumsq_late: Optional[torch.Tensor] = None
 
     def reduce_scalar_(self, t: torch.Tensor) -> None:
         self.shards.all_reduce_(t)
@@ -284,36 +311,90 @@ class ShardedHotPath(HotPath):
             self._g_red[slot] = t
         return t
 
+    # ---- span-level building blocks (one kernel launch each; no barrier) ----------------------------------
+    def _span(self, t: Optional[torch.Tensor], i: int) -> Optional[torch.Tensor]:
+        """Span i of a tensor that covers this rank's whole local shard."""
+        if t is None:
+            return None
+        _, off, cnt = self.shards.spans[i]
+        return t if (t.numel() == cnt and self.shards.parts == 1) else t[off:off + cnt]
+
+    def _p_span(self, p, i: int) -> torch.Tensor:
+        """p: the local fp32 shard (all spans concatenated), or one tensor per span (views of a full weight vector)."""
+        return p[i] if isinstance(p, (list, tuple)) else self._span(p, i)
+
+    def reduce_span(self, x: "PeerExchange", i: int, g: "SymBuffer", *, average: bool = True,
+                    g_red: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+                    sumsq: Optional[torch.Tensor] = None, fisher: Optional[torch.Tensor] = None,
+                    fisher_divisor: float = 1.0, max_ctas: int = 0) -> None:
+        capi.peer_reduce(g.buf, g.tensor.dtype, x.span_geom(i), x.reduce_transport, average,
+                         g_red=self._span(g_red, i), mask=self._span(mask, i), sumsq=sumsq,
+                         fisher=self._span(fisher, i), fisher_divisor=fisher_divisor, max_ctas=max_ctas)
+
+    def update_span(self, x: "PeerExchange", i: int, p, a: "capi.UpdateArgs", *, g, g_red, weights, weights_bf16, mask,
+                    use_ema: bool, clip, average: bool = True, prepare: bool = True, max_ctas: int = 0) -> None:
+        """K3 (+ exchange) on span i.  prepare=False: an earlier span of the SAME optimizer step already ran the
+        scalar-prep kernel (step counter, bias corrections, clip coefficient): reuse its results."""
+        sgd = self.opt.kind == "sgd"
+        need_consts = clip is not None or self.step_dev is not None or self.lr_table is not None or not prepare
+        flags = a.flags
+        if not prepare:
+            a.flags = flags | capi.F_REUSE_CONSTS
+        try:
+            capi.peer_fused_update(
+                self._p_span(p, i), x.span_geom(i), a, g_red=self._span(g_red, i), g=g.buf if g_red is None else None,
+                g_dtype=g.tensor.dtype if g_red is None else torch.float32, g_transport=x.reduce_transport,
+                average=average, m=None if (sgd and self.opt.momentum == 0.0) else self._span(self.m, i),
+                v=None if sgd else self._span(self.v, i), mask=self._span(mask, i),
+                ema=self._span(self.slow, i) if use_ema else None, bc_f32=None if weights is None else weights.buf,
+                bc_bf16=None if weights_bf16 is None else weights_bf16.buf, bc_transport=x.push_transport,
+                clip_sumsq=clip, step_counter=self.step_dev if prepare else None,
+                consts_scratch=self._consts_dev if need_consts else None, max_ctas=max_ctas)
+        finally:
+            a.flags = flags
+
     def dp_fisher_accumulate(self, which: str, g: "SymBuffer", divisor: float, *, average: bool = True,
                              keep: Optional[str] = None, clip_max_norm: Optional[float] = None) -> None:
-        """K1 on the data-parallel mean gradient: barrier, then ONE kernel that pulls this shard of every
+        """K1 on the data-parallel mean gradient: barrier, then ONE kernel (per span) that pulls this shard of every
         rank's `g`, averages and accumulates F += gbar**2 / divisor (keep="slot": the reduced shard is also left in
         `self.reduced(slot)` for a following step on the same gradients).  With `clip_max_norm` (DDPM Fisher of
         the clipped gradient) the norm has to be global first: reduce + sum of squares, summed across ranks on
         the barrier, then the shard-local clipped K1."""
         x = self._need_xchg()
         acc = self.buffer({"forget": "forget_fisher", "remain": "remain_fisher"}.get(which, which))
+        spans = range(len(self.shards.spans))
         x.barrier()
         if clip_max_norm is None:
-            capi.peer_reduce(g.buf, g.tensor.dtype, x.geom, x.reduce_transport, average, fisher=acc, fisher_divisor=divisor,
-                             g_red=self.reduced(keep) if keep else None)
+            for i in spans:
+                self.reduce_span(x, i, g, average=average, fisher=acc, fisher_divisor=divisor,
+                                 g_red=self.reduced(keep) if keep else None)
             self._t("fisher_accum")
             x.barrier()
             return
         red = self.reduced(keep or "_clip")
         self.sumsq.zero_()
-        capi.peer_reduce(g.buf, g.tensor.dtype, x.geom, x.reduce_transport, average, g_red=red, sumsq=self.sumsq)
+        for i in spans:
+            self.reduce_span(x, i, g, average=average, g_red=red, sumsq=self.sumsq)
         x.barrier(self.sumsq, self.sumsq)
         capi.fisher_accum(acc, red, divisor, clip_sumsq=self.sumsq, clip_max_norm=clip_max_norm)
         self._t("fisher_accum_clipped")
 
-    def dp_step(self, p: torch.Tensor, g, *, weights: Optional["SymBuffer"] = None,
+    def _step_flags(self, mask, mask_order: str) -> int:
+        flags = 0
+        if mask is not None:
+            flags |= capi.F_MASK if mask_order == "mask_then_clip" else capi.F_MASK_AFTER_CLIP
+        if self.step_dev is None and self.opt.kind == "sgd" and self.opt.momentum != 0.0 and not self.has("m"):
+            flags |= capi.F_SGD_FIRST_STEP
+        return flags
+
+    def dp_step(self, p, g, *, weights: Optional["SymBuffer"] = None,
                 weights_bf16: Optional["SymBuffer"] = None, mask: Optional[torch.Tensor] = None,
                 mask_order: str = "mask_then_clip", max_norm: Optional[float] = None, ema: bool = False,
                 lr: Optional[float] = None, average: bool = True, keep: str = "_step") -> None:
         """One optimizer step of the sharded data-parallel loop.
 
-        p: this rank's fp32 weight shard (a view of `weights.tensor[lo:hi]`, or the fp32 master shard in bf16 mode).
+        p: this rank's fp32 weight shard (a view of `weights.tensor[lo:hi]`, the fp32 master shard in bf16 mode, or
+           one tensor per span).
         g: a SymBuffer holding every rank's FULL gradient (reduced inside the kernels), or a local fp32
            tensor with this rank's already reduced shard (e.g. `self.reduced(slot)` left by dp_fisher_accumulate).
         weights / weights_bf16: full-vector symmetric buffers that receive the updated shard on EVERY rank.
@@ -321,12 +402,8 @@ class ShardedHotPath(HotPath):
         Clip:    barrier -> reduce + masked sum of squares -> barrier carrying the norm -> K3 + push -> barrier."""
         x = self._need_xchg()
         from_peers = isinstance(g, SymBuffer)
-        flags = 0
-        if mask is not None:
-            flags |= capi.F_MASK if mask_order == "mask_then_clip" else capi.F_MASK_AFTER_CLIP
-        sgd = self.opt.kind == "sgd"
-        if self.step_dev is None and sgd and self.opt.momentum != 0.0 and not self.has("m"):
-            flags |= capi.F_SGD_FIRST_STEP
+        flags = self._step_flags(mask, mask_order)
+        spans = range(len(self.shards.spans))
         clip = None
         g_red = None if from_peers else g
         if from_peers:
@@ -336,8 +413,8 @@ class ShardedHotPath(HotPath):
             self.sumsq.zero_()
             if from_peers:
                 g_red = self.reduced(keep)
-                capi.peer_reduce(g.buf, g.tensor.dtype, x.geom, x.reduce_transport, average, g_red=g_red, mask=norm_mask,
-                                 sumsq=self.sumsq)
+                for i in spans:
+                    self.reduce_span(x, i, g, average=average, g_red=g_red, mask=norm_mask, sumsq=self.sumsq)
             else:
                 capi.masked_sumsq(g_red, norm_mask, self.sumsq)
             self._t("masked_sumsq")
@@ -346,17 +423,82 @@ class ShardedHotPath(HotPath):
         self.step_count += 1
         a = self._args(flags, ema, max_norm, lr)
         use_ema = ema and self.ema_mode != "none"
-        capi.peer_fused_update(
-            p, x.geom, a, g_red=g_red, g=g.buf if g_red is None else None,
-            g_dtype=g.tensor.dtype if g_red is None else torch.float32, g_transport=x.reduce_transport, average=average,
-            m=None if (sgd and self.opt.momentum == 0.0) else self.m, v=None if sgd else self.v, mask=mask,
-            ema=self.slow if use_ema else None, bc_f32=None if weights is None else weights.buf,
-            bc_bf16=None if weights_bf16 is None else weights_bf16.buf, bc_transport=x.push_transport, clip_sumsq=clip,
-            step_counter=self.step_dev,
-            consts_scratch=self._consts_dev if (clip is not None or self.step_dev is not None
-                                                or self.lr_table is not None) else None)
+        for k, i in enumerate(spans):
+            self.update_span(x, i, p, a, g=g, g_red=g_red, weights=weights, weights_bf16=weights_bf16, mask=mask,
+                             use_ema=use_ema, clip=clip, average=average, prepare=k == 0)
         self._t("fused_update_ema" if use_ema else "fused_update")
         x.barrier()                                       # gradients may be overwritten; every weight store has landed
+
+    # ---- the same step, pipelined against the backward pass (ShardGroup(parts=2) + OverlappedBackward) ----------
+    def dp_begin_step(self, ov: "OverlappedBackward", p, g: "SymBuffer", *, weights: Optional["SymBuffer"] = None,
+                      weights_bf16: Optional["SymBuffer"] = None, mask: Optional[torch.Tensor] = None,
+                      mask_order: str = "mask_then_clip", max_norm: Optional[float] = None, ema: bool = False,
+                      lr: Optional[float] = None, average: bool = True, keep: str = "_step") -> None:
+        """Call BEFORE `loss.backward()`.  As soon as backward has finished the late half of the flat vector (its
+        gradients come first), this rank's span of that half is exchanged on a side stream, by a few CTAs, while
+        backward keeps producing the early half:
+          unclipped step   barrier -> reduce + K3 [+ EMA] + weight push of the late span (one kernel)
+          clipped step     barrier -> reduce + masked sum of squares of the late span (the update needs the whole norm)
+        `dp_finish_step()` after backward does the early span and whatever had to wait for the norm."""
+        if self.shards.parts != 2:
+            raise capi.SfrError(capi.ERR_ARG, "dp_begin_step", "needs a ShardGroup with parts=2")
+        self._need_xchg()
+        rec = dict(ov=ov, p=p, g=g, weights=weights, weights_bf16=weights_bf16, mask=mask, mask_order=mask_order,
+                   max_norm=max_norm, ema=ema, lr=lr, average=average, keep=keep, a=None)
+        self._pending = rec
+        if self._sumsq_late is None:
+            self._sumsq_late = torch.zeros(1, dtype=torch.float64, device=self.device)
+        use_ema = ema and self.ema_mode != "none"
+        norm_mask = mask if (mask is not None and mask_order == "mask_then_clip") else None
+
+        def late():
+            xs = ov.xchg
+            xs.barrier()                                  # every rank's backward is past the late half
+            if max_norm is not None:
+                self._sumsq_late.zero_()
+                self.reduce_span(xs, 1, g, average=average, g_red=self.reduced(keep), mask=norm_mask,
+                                 sumsq=self._sumsq_late, max_ctas=ov.max_ctas)
+            else:
+                self.step_count += 1
+                rec["a"] = self._args(self._step_flags(mask, mask_order), ema, None, lr)
+                self.update_span(xs, 1, p, rec["a"], g=g, g_red=None, weights=weights, weights_bf16=weights_bf16,
+                                 mask=mask, use_ema=use_ema, clip=None, average=average, prepare=True,
+                                 max_ctas=ov.max_ctas)
+
+        ov.arm(late)
+
+    def dp_finish_step(self) -> None:
+        """Call AFTER `loss.backward()`: the early span, the norm (clipped steps), the join with the side stream."""
+        rec, self._pending = self._pending, None
+        if rec is None:
+            raise capi.SfrError(capi.ERR_ARG, "dp_finish_step", "no step in flight (dp_begin_step)")
+        x, ov = self._need_xchg(), rec["ov"]
+        ov.flush()                                        # (a pass in which some late parameter got no gradient)
+        g, p, mask, max_norm = rec["g"], rec["p"], rec["mask"], rec["max_norm"]
+        use_ema = rec["ema"] and self.ema_mode != "none"
+        x.barrier()                                       # every rank's backward has written ALL its gradients
+        if max_norm is not None:
+            norm_mask = mask if (mask is not None and rec["mask_order"] == "mask_then_clip") else None
+            g_red = self.reduced(rec["keep"])
+            self.sumsq.zero_()
+            self.reduce_span(x, 0, g, average=rec["average"], g_red=g_red, mask=norm_mask, sumsq=self.sumsq)
+            ov.join()
+            self.sumsq.add_(self._sumsq_late)
+            self._t("masked_sumsq")
+            x.barrier(self.sumsq, self.sumsq)
+            self.step_count += 1
+            a = self._args(self._step_flags(mask, rec["mask_order"]), rec["ema"], max_norm, rec["lr"])
+            for k, i in enumerate((0, 1)):
+                self.update_span(x, i, p, a, g=g, g_red=g_red, weights=rec["weights"],
+                                 weights_bf16=rec["weights_bf16"], mask=mask, use_ema=use_ema, clip=self.sumsq,
+                                 average=rec["average"], prepare=k == 0)
+        else:
+            ov.join()                                     # the late span's prep kernel has set this step's scalars
+            self.update_span(x, 0, p, rec["a"], g=g, g_red=None, weights=rec["weights"],
+                             weights_bf16=rec["weights_bf16"], mask=mask, use_ema=use_ema, clip=None,
+                             average=rec["average"], prepare=False)
+        self._t("fused_update_ema" if use_ema else "fused_update")
+        x.barrier()
 
     def dp_forget_step(self, p, g, *, mask: Optional[torch.Tensor] = None, use_mask: bool = True, **kw) -> None:
         """grad *= mask ; clip ; step on the data-parallel mean gradient (DiT/forget.py:285-299 under DataParallel)."""
@@ -367,6 +509,57 @@ class ShardedHotPath(HotPath):
     def dp_remain_step(self, p, g, *, ema: bool = True, **kw) -> None:
         """[clip ;] step ; EMA on the data-parallel mean gradient (DiT/forget.py:310-322 under DataParallel)."""
         self.dp_step(p, g, mask=None, ema=ema, **kw)
+
+
+class OverlappedBackward:
+    """Fires a callback INSIDE `loss.backward()`, on a side stream, at the moment the late half of the flat gradient
+    is final: autograd produces gradients roughly in reverse parameter order, so every parameter that reaches into
+    [boundary, n) has accumulated its gradient long before the first layers have.  The callback (armed per backward
+    pass by ShardedHotPath.dp_begin_step) launches the exchange of that half with few CTAs (`max_ctas`), so it runs
+    beside the rest of the backward pass instead of after it.  `xchg` is the exchange the side stream uses (its own
+    barrier pad: PeerExchange.sibling()).  Works under CUDA-graph capture: the side stream forks from and joins the
+    capturing stream."""
+
+    def __init__(self, flat, shards: ShardGroup, xchg: "PeerExchange", max_ctas: int = 32):
+        if shards.parts != 2:
+            raise ValueError("OverlappedBackward pipelines two parts: ShardGroup(..., parts=2)")
+        self.xchg, self.max_ctas = xchg, int(max_ctas)
+        self.device = flat.device
+        self.side = torch.cuda.Stream(device=self.device)
+        # first global element of part 1 = padded length / 2 (the same on every rank)
+        self.boundary = flat.n_padded // 2
+        late = [prm for seg, prm in zip(flat.layout, flat._train_params) if seg.offset + seg.numel > self.boundary]
+        self._need, self._seen, self._fn, self._fired = len(late), 0, None, False
+        self._handles = [prm.register_post_accumulate_grad_hook(self._hook) for prm in late]
+
+    def arm(self, fn) -> None:
+        self._fn, self._seen, self._fired = fn, 0, False
+
+    def _hook(self, _param) -> None:
+        self._seen += 1
+        if self._seen == self._need and self._fn is not None and not self._fired:
+            self._fire()
+
+    def _fire(self) -> None:
+        self._fired = True
+        main = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(main)                        # the late gradients precede this point of the backward pass
+        with torch.cuda.stream(self.side):
+            self._fn()
+
+    def flush(self) -> None:
+        """After backward: if a late parameter received no gradient this pass the hook count never completed."""
+        if self._fn is not None and not self._fired:
+            self._fire()
+
+    def join(self) -> None:
+        torch.cuda.current_stream(self.device).wait_stream(self.side)
+        self._fn = None
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
 
 
 class SymBuffer:
@@ -395,17 +588,19 @@ class PeerExchange:
     def __init__(self, shards: ShardGroup, device, transport: str = "auto", timeout_s: float = 30.0):
         if shards.world > capi.MAX_PEERS:
             raise capi.SfrError(capi.ERR_ARG, "PeerExchange", f"at most {capi.MAX_PEERS} ranks (one NVSwitch box)")
-        if shards.n_local and shards.lo % 16:
+        if any(c and g % 16 for g, _, c in shards.spans):
             raise capi.SfrError(capi.ERR_ALIGN, "PeerExchange", "shard starts must be multiples of 16 elements")
         self.shards = shards
         self.device = torch.device(device)
         self.group = shards.group if shards.group is not None else dist.group.WORLD
         self.timeout_ns = int(timeout_s * 1e9)
         self._want = transport
-        # what "auto" means when the fabric has multicast (measured, tools/xchg_bench.py -> profiles/r2_xchg_*.jsonl)
-        self._auto = (capi.XP_P2P, capi.XP_P2P) if shards.world <= 2 else (capi.XP_MULTIMEM, capi.XP_MULTIMEM)
+        # what "auto" means (measured, tools/xchg_bench.py -> profiles/r2_xchg_n*.jsonl): TMA bulk copies beat the
+        # load/store transports and NCCL at every world size tried, for every op
+        self._auto = (capi.XP_TMA, capi.XP_TMA)
         self._buffers: List[SymBuffer] = []
-        self.geom = capi.PeerGeom(shards.world, shards.rank, shards.lo, shards.n_local)
+        self._geoms = [capi.PeerGeom(shards.world, shards.rank, g, c) for g, _, c in shards.spans]
+        self.geom = self._geoms[0]                          # (the only one unless the ShardGroup has parts > 1)
         self.pad = self.alloc(capi.peer_pad_bytes() // 8, torch.int64)         # zero-filled by alloc()
         self._vals = torch.zeros(8, dtype=torch.float64, device=self.device)
         self.barriers = 0
@@ -431,8 +626,8 @@ class PeerExchange:
             return capi.XP_MULTIMEM
         if want != "auto":
             raise capi.SfrError(capi.ERR_ARG, "PeerExchange", f"unknown transport {want!r}")
-        if not mc:
-            return capi.XP_P2P
+        if self._auto[which] == capi.XP_MULTIMEM and not mc:
+            return capi.XP_TMA
         return self._auto[which]
 
     @property
@@ -448,6 +643,17 @@ class PeerExchange:
         names = {capi.XP_P2P: "p2p", capi.XP_MULTIMEM: "multimem", capi.XP_TMA: "tma"}
         r, p = names[self.reduce_transport], names[self.push_transport]
         return r if r == p else f"{r}+{p}"
+
+    def span_geom(self, i: int) -> "capi.PeerGeom":
+        return self._geoms[i]
+
+    def sibling(self) -> "PeerExchange":
+        """A second exchange over the same shards with its OWN barrier pad, for kernels on another stream
+        (a pad serves one stream at a time).  Collective."""
+        other = PeerExchange(self.shards, self.device, transport=self._want, timeout_s=self.timeout_ns / 1e9)
+        other._auto = self._auto
+        other._buffers.extend(self._buffers[1:])            # same data buffers: "auto" sees the same multicast support
+        return other
 
     def alloc(self, numel: int, dtype: torch.dtype) -> SymBuffer:
         """Collective: every rank allocates the same buffer (zero-filled) and maps the others'."""
