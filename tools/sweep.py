@@ -106,6 +106,16 @@ def main():
             emit("fused_update_adamw_masked_clip", n, dtype, 25 + sg,
                  timer(lambda: hp.forget_step(p, g, max_norm=None)))
             emit("fused_update_adamw_ema", n, dtype, 32 + sg, timer(lambda: hp.remain_step(p, g, ema=True)))
+            if n <= hp.coop_max_elems:
+                # clipped forget step (norm + update): one cooperative launch vs memset + norm + scalar prep + update
+                emit("clipped_forget_step_one_cooperative_launch", n, dtype, 30 + 2 * sg,
+                     timer(lambda: hp.forget_step(p, g, max_norm=1.0)),
+                     note="sfr_clipped_update: zero + masked sum of squares + grid barrier + AdamW; g is read twice")
+                keep = hp.coop_max_elems
+                hp.coop_max_elems = 0
+                emit("clipped_forget_step_four_launches", n, dtype, 30 + 2 * sg,
+                     timer(lambda: hp.forget_step(p, g, max_norm=1.0)))
+                hp.coop_max_elems = keep
         if n <= 1_000_000_000:   # per-sample FIM, 4 rows (16 B/elem of gradient rows)
             n_pad = (n + 7) // 8 * 8          # row stride must keep every row 16-byte aligned
             rows = torch.empty(4, n_pad, device=dev).normal_(0, 1e-2, generator=gen)[:, :n]
@@ -130,9 +140,13 @@ def main():
             topk = torch.empty(n, dtype=torch.uint8, device=dev)
             k = n // 2
             emit("topk_select_total", n, "-", 13, timer(lambda: hp.topk_mask(g32, k, out=topk)),
-                 note="two-pass form: pass 1 writes the provisional mask, apply resolves the staged candidates; "
-                      "13 B/elem is the three-read algorithmic figure, actual traffic ~9 B/elem")
+                 note="product form: two-pass select, apply stage as ONE cooperative launch, the whole select replayed "
+                      "from a CUDA graph; 13 B/elem is the three-read algorithmic figure, actual traffic ~9 B/elem")
             assert int(topk.sum()) == k
+            hp.select_graphs = False
+            emit("topk_select_total_eager_launches", n, "-", 13, timer(lambda: hp.topk_mask(g32, k, out=topk)),
+                 note="the same kernels launched one by one (no graph)")
+            hp.select_graphs = True
             hp.select_two_pass = False
             emit("topk_select_total_three_reads", n, "-", 13, timer(lambda: hp.topk_mask(g32, k, out=topk)),
                  note="hist pass 0 + pass 1 + streaming apply = 4+4+4+1 B/elem")

@@ -332,11 +332,18 @@ class ShardedHotPath(HotPath):
                          fisher=self._span(fisher, i), fisher_divisor=fisher_divisor, max_ctas=max_ctas)
 
     def update_span(self, x: "PeerExchange", i: int, p, a: "capi.UpdateArgs", *, g, g_red, weights, weights_bf16, mask,
-                    use_ema: bool, clip, average: bool = True, prepare: bool = True, max_ctas: int = 0) -> None:
-        """K3 (+ exchange) on span i.  prepare=False: an earlier span of the SAME optimizer step already ran the
-        scalar-prep kernel (step counter, bias corrections, clip coefficient): reuse its results."""
+                    use_ema: bool, clip, average: bool = True, consts: str = "auto", max_ctas: int = 0) -> None:
+        """K3 (+ exchange) on span i.  consts: how the step's scalars (step counter, bias corrections, clip
+        coefficient) reach the kernel —
+          "auto"     one launch per optimizer step: by value unless a clip / device counter / device LR needs the
+                     scalar-prep kernel;
+          "prepare"  first of several launches of ONE optimizer step: always run the prep kernel (it leaves the
+                     scalars in device scratch and advances the device step counter once);
+          "reuse"    a later launch of the same step: read that scratch, advance nothing."""
         sgd = self.opt.kind == "sgd"
-        need_consts = clip is not None or self.step_dev is not None or self.lr_table is not None or not prepare
+        prepare = consts != "reuse"
+        need_consts = (consts != "auto" or clip is not None or self.step_dev is not None
+                       or self.lr_table is not None)
         flags = a.flags
         if not prepare:
             a.flags = flags | capi.F_REUSE_CONSTS
@@ -423,9 +430,11 @@ class ShardedHotPath(HotPath):
         self.step_count += 1
         a = self._args(flags, ema, max_norm, lr)
         use_ema = ema and self.ema_mode != "none"
+        several = len(spans) > 1
         for k, i in enumerate(spans):
             self.update_span(x, i, p, a, g=g, g_red=g_red, weights=weights, weights_bf16=weights_bf16, mask=mask,
-                             use_ema=use_ema, clip=clip, average=average, prepare=k == 0)
+                             use_ema=use_ema, clip=clip, average=average,
+                             consts="auto" if not several else ("prepare" if k == 0 else "reuse"))
         self._t("fused_update_ema" if use_ema else "fused_update")
         x.barrier()                                       # gradients may be overwritten; every weight store has landed
 
@@ -462,7 +471,7 @@ class ShardedHotPath(HotPath):
                 self.step_count += 1
                 rec["a"] = self._args(self._step_flags(mask, mask_order), ema, None, lr)
                 self.update_span(xs, 1, p, rec["a"], g=g, g_red=None, weights=weights, weights_bf16=weights_bf16,
-                                 mask=mask, use_ema=use_ema, clip=None, average=average, prepare=True,
+                                 mask=mask, use_ema=use_ema, clip=None, average=average, consts="prepare",
                                  max_ctas=ov.max_ctas)
 
         ov.arm(late)
@@ -491,12 +500,12 @@ class ShardedHotPath(HotPath):
             for k, i in enumerate((0, 1)):
                 self.update_span(x, i, p, a, g=g, g_red=g_red, weights=rec["weights"],
                                  weights_bf16=rec["weights_bf16"], mask=mask, use_ema=use_ema, clip=self.sumsq,
-                                 average=rec["average"], prepare=k == 0)
+                                 average=rec["average"], consts="prepare" if k == 0 else "reuse")
         else:
             ov.join()                                     # the late span's prep kernel has set this step's scalars
             self.update_span(x, 0, p, rec["a"], g=g, g_red=None, weights=rec["weights"],
                              weights_bf16=rec["weights_bf16"], mask=mask, use_ema=use_ema, clip=None,
-                             average=rec["average"], prepare=False)
+                             average=rec["average"], consts="reuse")
         self._t("fused_update_ema" if use_ema else "fused_update")
         x.barrier()
 
