@@ -683,9 +683,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         # stdout carries exactly one JSON line: NCCL's init lines (rank / nranks, transports) go to stderr
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ["NCCL_DEBUG"] = os.environ.get("SFR_NCCL_DEBUG", "INFO")
+        os.environ["NCCL_DEBUG_SUBSYS"] = os.environ.get("SFR_NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:

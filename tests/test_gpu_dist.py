@@ -259,12 +259,12 @@ def _overlapped_backward(rank, world, dev):
     import sfron_b200 as sfr
     from sfron_b200.dist import OverlappedBackward, PeerExchange, ShardGroup, ShardedHotPath
     from oracle import sfron_oracle as O
-    for graphed in (False, True):
+    for graphed, parts in ((False, 2), (True, 2), (False, 3), (True, 3)):
         torch.manual_seed(0)                                # identical weights on every rank
         model = nn.Sequential(nn.Linear(48, 160), nn.Tanh(), nn.Linear(160, 160), nn.Tanh(), nn.Linear(160, 24)).to(dev)
         n = sum(p.numel() for p in model.parameters())
-        n_pad = -(-n // (32 * world)) * (32 * world)
-        sg = ShardGroup(n, padded_len=n_pad, parts=2)
+        n_pad = -(-n // (16 * parts * world)) * (16 * parts * world)
+        sg = ShardGroup(n, padded_len=n_pad, parts=parts)
         xchg = PeerExchange(sg, dev, transport="tma", timeout_s=20.0)
         sym = {}
 
@@ -272,12 +272,12 @@ def _overlapped_backward(rank, world, dev):
             sym[role] = xchg.alloc(numel, dtype)
             return sym[role].tensor
 
-        flat = sfr.FlatParams(model, dev, pad_multiple=32 * world, alloc=alloc)
+        flat = sfr.FlatParams(model, dev, pad_multiple=16 * parts * world, alloc=alloc)
         theta0 = flat.p.detach().cpu().clone()
         hp = ShardedHotPath(sg, dev, sfr.OptConfig(kind="adam", lr=1e-3), ema_mode="ddpm", ema_a=1e-2)
         hp.attach_exchange(xchg)
         ov = OverlappedBackward(flat, sg, xchg.sibling(), max_ctas=4)
-        assert 0 < ov._need < len(flat._train_params)
+        assert all(0 < k <= len(flat._train_params) for k in ov._need[1:]) and ov._need[0] == 0
         mask = torch.rand(n, generator=torch.Generator().manual_seed(5)) < 0.5
         hp.set_buffer("mask", sg.local(mask.to(torch.uint8)).to(dev))
         p_views = [flat.p[g:g + c] for g, _, c in sg.spans]
@@ -339,10 +339,10 @@ def _overlapped_backward(rank, world, dev):
             assert _close(hp.slow, sg.local(want_slow))
             eager_final = flat.p.detach().cpu().clone()
             dist.barrier()
-            torch.save(eager_final, f"/tmp/_sfr_ov_{rank}.pt")
+            torch.save(eager_final, f"/tmp/_sfr_ov_{rank}_{parts}.pt")
         else:
             # same data, same kernels, replayed: the weights of the eager run
-            assert _close(flat.p, torch.load(f"/tmp/_sfr_ov_{rank}.pt"), 1e-6)
+            assert _close(flat.p, torch.load(f"/tmp/_sfr_ov_{rank}_{parts}.pt"), 1e-6)
             assert int(hp.step_dev) == 8
         ov.remove()
 

@@ -121,7 +121,7 @@ def run_ours(args, dev, ac, rank, world):
         import torch.distributed as dist
         from sfron_b200.dist import PeerExchange, ShardGroup, ShardedHotPath
         n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
-        parts = 2 if overlap else 1
+        parts = args.overlap_parts if overlap else 1
         n_pad = -(-n_train // (16 * world * parts)) * (16 * world * parts)
         sg = ShardGroup(n_train, padded_len=n_pad, parts=parts)
         xchg = PeerExchange(sg, dev, transport=args.dp_exchange.partition(":")[2] or "auto")
@@ -339,6 +339,8 @@ def main():
                          "around the shard-local kernels; bucketed: NCCL all-reduce in buckets started from autograd "
                          "hooks while backward still runs (sfron_b200.dist.BucketedGradReducer)")
     ap.add_argument("--bucket-mb", type=int, default=64)
+    ap.add_argument("--overlap-parts", type=int, default=4,
+                    help="peer-overlap: pieces the flat vector is cut into; all but the first are exchanged during backward")
     ap.add_argument("--overlap-ctas", type=int, default=32,
                     help="peer-overlap[:transport]: CTAs of the exchange kernels that run beside the backward pass")
     ap.add_argument("--out", default=None)

@@ -326,13 +326,14 @@ class ShardedHotPath(HotPath):
     def reduce_span(self, x: "PeerExchange", i: int, g: "SymBuffer", *, average: bool = True,
                     g_red: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
                     sumsq: Optional[torch.Tensor] = None, fisher: Optional[torch.Tensor] = None,
-                    fisher_divisor: float = 1.0, max_ctas: int = 0) -> None:
-        capi.peer_reduce(g.buf, g.tensor.dtype, x.span_geom(i), x.reduce_transport, average,
+                    fisher_divisor: float = 1.0, max_ctas: int = 0, xp: Optional[int] = None) -> None:
+        capi.peer_reduce(g.buf, g.tensor.dtype, x.span_geom(i), x.reduce_transport if xp is None else xp, average,
                          g_red=self._span(g_red, i), mask=self._span(mask, i), sumsq=sumsq,
                          fisher=self._span(fisher, i), fisher_divisor=fisher_divisor, max_ctas=max_ctas)
 
     def update_span(self, x: "PeerExchange", i: int, p, a: "capi.UpdateArgs", *, g, g_red, weights, weights_bf16, mask,
-                    use_ema: bool, clip, average: bool = True, consts: str = "auto", max_ctas: int = 0) -> None:
+                    use_ema: bool, clip, average: bool = True, consts: str = "auto", max_ctas: int = 0,
+                    xp: Optional[int] = None) -> None:
         """K3 (+ exchange) on span i.  consts: how the step's scalars (step counter, bias corrections, clip
         coefficient) reach the kernel —
           "auto"     one launch per optimizer step: by value unless a clip / device counter / device LR needs the
@@ -347,14 +348,20 @@ class ShardedHotPath(HotPath):
         flags = a.flags
         if not prepare:
             a.flags = flags | capi.F_REUSE_CONSTS
+        pushes = weights is not None or weights_bf16 is not None
+        g_xp, bc_xp = x.reduce_transport, x.push_transport
+        if g_red is None and pushes:
+            g_xp = bc_xp = x.fused_transport              # one kernel, both directions
+        if xp is not None:
+            g_xp = bc_xp = xp
         try:
             capi.peer_fused_update(
                 self._p_span(p, i), x.span_geom(i), a, g_red=self._span(g_red, i), g=g.buf if g_red is None else None,
-                g_dtype=g.tensor.dtype if g_red is None else torch.float32, g_transport=x.reduce_transport,
+                g_dtype=g.tensor.dtype if g_red is None else torch.float32, g_transport=g_xp,
                 average=average, m=None if (sgd and self.opt.momentum == 0.0) else self._span(self.m, i),
                 v=None if sgd else self._span(self.v, i), mask=self._span(mask, i),
                 ema=self._span(self.slow, i) if use_ema else None, bc_f32=None if weights is None else weights.buf,
-                bc_bf16=None if weights_bf16 is None else weights_bf16.buf, bc_transport=x.push_transport,
+                bc_bf16=None if weights_bf16 is None else weights_bf16.buf, bc_transport=bc_xp,
                 clip_sumsq=clip, step_counter=self.step_dev if prepare else None,
                 consts_scratch=self._consts_dev if need_consts else None, max_ctas=max_ctas)
         finally:
@@ -443,14 +450,14 @@ class ShardedHotPath(HotPath):
                       weights_bf16: Optional["SymBuffer"] = None, mask: Optional[torch.Tensor] = None,
                       mask_order: str = "mask_then_clip", max_norm: Optional[float] = None, ema: bool = False,
                       lr: Optional[float] = None, average: bool = True, keep: str = "_step") -> None:
-        """Call BEFORE `loss.backward()`.  As soon as backward has finished the late half of the flat vector (its
-        gradients come first), this rank's span of that half is exchanged on a side stream, by a few CTAs, while
-        backward keeps producing the early half:
-          unclipped step   barrier -> reduce + K3 [+ EMA] + weight push of the late span (one kernel)
-          clipped step     barrier -> reduce + masked sum of squares of the late span (the update needs the whole norm)
-        `dp_finish_step()` after backward does the early span and whatever had to wait for the norm."""
-        if self.shards.parts != 2:
-            raise capi.SfrError(capi.ERR_ARG, "dp_begin_step", "needs a ShardGroup with parts=2")
+        """Call BEFORE `loss.backward()`.  The flat vector is cut into `parts` pieces; backward finishes the LAST piece
+        first.  As soon as a piece other than the first is final on this rank, this rank's span of it is exchanged
+        on a side stream, by a few CTAs, while backward keeps producing the earlier pieces:
+          unclipped step   barrier -> reduce + K3 [+ EMA] + weight push of the span (one kernel)
+          clipped step     barrier -> reduce + masked sum of squares of the span (the update needs the whole norm)
+        `dp_finish_step()` after backward does the first piece and whatever had to wait for the norm."""
+        if self.shards.parts < 2:
+            raise capi.SfrError(capi.ERR_ARG, "dp_begin_step", "needs a ShardGroup with parts >= 2")
         self._need_xchg()
         rec = dict(ov=ov, p=p, g=g, weights=weights, weights_bf16=weights_bf16, mask=mask, mask_order=mask_order,
                    max_norm=max_norm, ema=ema, lr=lr, average=average, keep=keep, a=None)
@@ -459,25 +466,29 @@ class ShardedHotPath(HotPath):
             self._sumsq_late = torch.zeros(1, dtype=torch.float64, device=self.device)
         use_ema = ema and self.ema_mode != "none"
         norm_mask = mask if (mask is not None and mask_order == "mask_then_clip") else None
+        last = self.shards.parts - 1
 
-        def late():
+        def late(part: int):
             xs = ov.xchg
-            xs.barrier()                                  # every rank's backward is past the late half
+            xs.barrier()                                  # every rank's backward is past this piece
             if max_norm is not None:
-                self._sumsq_late.zero_()
-                self.reduce_span(xs, 1, g, average=average, g_red=self.reduced(keep), mask=norm_mask,
-                                 sumsq=self._sumsq_late, max_ctas=ov.max_ctas)
+                if part == last:
+                    self._sumsq_late.zero_()
+                self.reduce_span(xs, part, g, average=average, g_red=self.reduced(keep), mask=norm_mask,
+                                 sumsq=self._sumsq_late, max_ctas=ov.max_ctas, xp=capi.XP_TMA)
             else:
-                self.step_count += 1
-                rec["a"] = self._args(self._step_flags(mask, mask_order), ema, None, lr)
-                self.update_span(xs, 1, p, rec["a"], g=g, g_red=None, weights=weights, weights_bf16=weights_bf16,
-                                 mask=mask, use_ema=use_ema, clip=None, average=average, consts="prepare",
-                                 max_ctas=ov.max_ctas)
+                if part == last:                          # the first piece to go prepares the step's scalars
+                    self.step_count += 1
+                    rec["a"] = self._args(self._step_flags(mask, mask_order), ema, None, lr)
+                self.update_span(xs, part, p, rec["a"], g=g, g_red=None, weights=weights, weights_bf16=weights_bf16,
+                                 mask=mask, use_ema=use_ema, clip=None, average=average,
+                                 consts="prepare" if part == last else "reuse", max_ctas=ov.max_ctas,
+                                 xp=capi.XP_TMA)          # few CTAs beside backward: the copy-engine transport
 
         ov.arm(late)
 
     def dp_finish_step(self) -> None:
-        """Call AFTER `loss.backward()`: the early span, the norm (clipped steps), the join with the side stream."""
+        """Call AFTER `loss.backward()`: the first piece, the norm (clipped steps), the join with the side stream."""
         rec, self._pending = self._pending, None
         if rec is None:
             raise capi.SfrError(capi.ERR_ARG, "dp_finish_step", "no step in flight (dp_begin_step)")
@@ -497,12 +508,12 @@ class ShardedHotPath(HotPath):
             x.barrier(self.sumsq, self.sumsq)
             self.step_count += 1
             a = self._args(self._step_flags(mask, rec["mask_order"]), rec["ema"], max_norm, rec["lr"])
-            for k, i in enumerate((0, 1)):
+            for i in range(self.shards.parts):
                 self.update_span(x, i, p, a, g=g, g_red=g_red, weights=rec["weights"],
                                  weights_bf16=rec["weights_bf16"], mask=mask, use_ema=use_ema, clip=self.sumsq,
-                                 average=rec["average"], consts="prepare" if k == 0 else "reuse")
+                                 average=rec["average"], consts="prepare" if i == 0 else "reuse")
         else:
-            ov.join()                                     # the late span's prep kernel has set this step's scalars
+            ov.join()                                     # the last piece's prep kernel has set this step's scalars
             self.update_span(x, 0, p, rec["a"], g=g, g_red=None, weights=rec["weights"],
                              weights_bf16=rec["weights_bf16"], mask=mask, use_ema=use_ema, clip=None,
                              average=rec["average"], consts="reuse")
@@ -521,45 +532,58 @@ class ShardedHotPath(HotPath):
 
 
 class OverlappedBackward:
-    """Fires a callback INSIDE `loss.backward()`, on a side stream, at the moment the late half of the flat gradient
-    is final: autograd produces gradients roughly in reverse parameter order, so every parameter that reaches into
-    [boundary, n) has accumulated its gradient long before the first layers have.  The callback (armed per backward
-    pass by ShardedHotPath.dp_begin_step) launches the exchange of that half with few CTAs (`max_ctas`), so it runs
-    beside the rest of the backward pass instead of after it.  `xchg` is the exchange the side stream uses (its own
-    barrier pad: PeerExchange.sibling()).  Works under CUDA-graph capture: the side stream forks from and joins the
-    capturing stream."""
+    """Fires a callback INSIDE `loss.backward()`, on a side stream, each time one more piece of the flat gradient is
+    final.  The vector is cut into `shards.parts` equal pieces; autograd produces gradients roughly in reverse
+    parameter order, so the pieces complete last-to-first, and a piece is final once every parameter that reaches
+    into it has accumulated its gradient.  The callback (armed per backward pass by ShardedHotPath.dp_begin_step)
+    launches the exchange of that piece with few CTAs (`max_ctas`), so it runs beside the rest of the backward
+    pass instead of after it; piece 0 is left to `dp_finish_step`.  `xchg` is the exchange the side stream uses (its
+    own barrier pad: PeerExchange.sibling()).  Works under CUDA-graph capture: the side stream forks from and
+    joins the capturing stream."""
 
     def __init__(self, flat, shards: ShardGroup, xchg: "PeerExchange", max_ctas: int = 32):
-        if shards.parts != 2:
-            raise ValueError("OverlappedBackward pipelines two parts: ShardGroup(..., parts=2)")
-        self.xchg, self.max_ctas = xchg, int(max_ctas)
+        if shards.parts < 2:
+            raise ValueError("OverlappedBackward pipelines parts >= 2: ShardGroup(..., parts=P)")
+        self.xchg, self.max_ctas, self.parts = xchg, int(max_ctas), shards.parts
         self.device = flat.device
         self.side = torch.cuda.Stream(device=self.device)
-        # first global element of part 1 = padded length / 2 (the same on every rank)
-        self.boundary = flat.n_padded // 2
-        late = [prm for seg, prm in zip(flat.layout, flat._train_params) if seg.offset + seg.numel > self.boundary]
-        self._need, self._seen, self._fn, self._fired = len(late), 0, None, False
-        self._handles = [prm.register_post_accumulate_grad_hook(self._hook) for prm in late]
+        piece = flat.n_padded // shards.parts              # the same cut on every rank
+        self._parts_of = {}                                # parameter -> the late pieces it reaches into
+        self._need = [0] * shards.parts
+        for seg, prm in zip(flat.layout, flat._train_params):
+            first, last = seg.offset // piece, (seg.offset + seg.numel - 1) // piece
+            mine = [k for k in range(max(first, 1), min(last, shards.parts - 1) + 1)]
+            if mine:
+                self._parts_of[prm] = mine
+                for k in mine:
+                    self._need[k] += 1
+        self._seen = [0] * shards.parts
+        self._next = shards.parts - 1                      # pieces fire in order P-1, P-2, ..., 1
+        self._fn = None
+        self._handles = [prm.register_post_accumulate_grad_hook(self._hook) for prm in self._parts_of]
 
     def arm(self, fn) -> None:
-        self._fn, self._seen, self._fired = fn, 0, False
+        self._fn, self._seen, self._next = fn, [0] * self.parts, self.parts - 1
 
-    def _hook(self, _param) -> None:
-        self._seen += 1
-        if self._seen == self._need and self._fn is not None and not self._fired:
-            self._fire()
+    def _hook(self, param) -> None:
+        if self._fn is None:
+            return
+        for k in self._parts_of[param]:
+            self._seen[k] += 1
+        while self._next >= 1 and self._seen[self._next] >= self._need[self._next]:
+            self._fire(self._next)
 
-    def _fire(self) -> None:
-        self._fired = True
+    def _fire(self, part: int) -> None:
+        self._next = part - 1
         main = torch.cuda.current_stream(self.device)
-        self.side.wait_stream(main)                        # the late gradients precede this point of the backward pass
+        self.side.wait_stream(main)                        # this piece's gradients precede this point of the backward pass
         with torch.cuda.stream(self.side):
-            self._fn()
+            self._fn(part)
 
     def flush(self) -> None:
-        """After backward: if a late parameter received no gradient this pass the hook count never completed."""
-        if self._fn is not None and not self._fired:
-            self._fire()
+        """After backward: pieces whose hook count never completed (a parameter without a gradient this pass)."""
+        while self._fn is not None and self._next >= 1:
+            self._fire(self._next)
 
     def join(self) -> None:
         torch.cuda.current_stream(self.device).wait_stream(self.side)
@@ -604,9 +628,12 @@ class PeerExchange:
         self.group = shards.group if shards.group is not None else dist.group.WORLD
         self.timeout_ns = int(timeout_s * 1e9)
         self._want = transport
-        # what "auto" means (measured, tools/xchg_bench.py -> profiles/r2_xchg_n*.jsonl): TMA bulk copies beat the
-        # load/store transports and NCCL at every world size tried, for every op
+        # what "auto" means (measured, tools/xchg_bench.py -> profiles/r2_xchg_n*.jsonl): TMA bulk copies match or beat
+        # the load/store transports and NCCL for every op at every world size tried; the ONE-kernel reduce + update +
+        # push is the exception from 4 ranks on — there the switch's fan-in / fan-out (multimem) halves the bytes per
+        # direction (8 ranks, fp32: 5.85 vs 7.07 ms)
         self._auto = (capi.XP_TMA, capi.XP_TMA)
+        self._auto_fused = capi.XP_MULTIMEM if shards.world >= 4 else capi.XP_TMA
         self._buffers: List[SymBuffer] = []
         self._geoms = [capi.PeerGeom(shards.world, shards.rank, g, c) for g, _, c in shards.spans]
         self.geom = self._geoms[0]                          # (the only one unless the ShardGroup has parts > 1)
@@ -638,6 +665,17 @@ class PeerExchange:
         if self._auto[which] == capi.XP_MULTIMEM and not mc:
             return capi.XP_TMA
         return self._auto[which]
+
+    @property
+    def fused_transport(self) -> int:
+        """Transport of the kernel that reduces, updates and pushes in one pass (both directions at once)."""
+        if self._want != "auto":
+            r, q = self._pick(0), self._pick(1)
+            return r if r == q else capi.XP_TMA
+        data = self._buffers[1:] or self._buffers
+        if self._auto_fused == capi.XP_MULTIMEM and not all(b.has_multicast for b in data):
+            return capi.XP_TMA
+        return self._auto_fused
 
     @property
     def reduce_transport(self) -> int:
