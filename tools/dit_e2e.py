@@ -339,7 +339,7 @@ def main():
                          "around the shard-local kernels; bucketed: NCCL all-reduce in buckets started from autograd "
                          "hooks while backward still runs (sfron_b200.dist.BucketedGradReducer)")
     ap.add_argument("--bucket-mb", type=int, default=64)
-    ap.add_argument("--overlap-parts", type=int, default=4,
+    ap.add_argument("--overlap-parts", type=int, default=8,
                     help="peer-overlap: pieces the flat vector is cut into; all but the first are exchanged during backward")
     ap.add_argument("--overlap-ctas", type=int, default=32,
                     help="peer-overlap[:transport]: CTAs of the exchange kernels that run beside the backward pass")

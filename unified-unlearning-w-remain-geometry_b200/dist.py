@@ -630,10 +630,10 @@ class PeerExchange:
         self._want = transport
         # what "auto" means (measured, tools/xchg_bench.py -> profiles/r2_xchg_n*.jsonl): TMA bulk copies match or beat
         # the load/store transports and NCCL for every op at every world size tried; the ONE-kernel reduce + update +
-        # push is the exception from 4 ranks on — there the switch's fan-in / fan-out (multimem) halves the bytes per
-        # direction (8 ranks, fp32: 5.85 vs 7.07 ms)
+        # push is the exception at 8 ranks — there the switch's fan-in / fan-out (multimem) halves the bytes per
+        # direction (fp32: 5.85 vs 7.07 ms; at 4 ranks TMA still wins, 5.96 vs 6.21 ms)
         self._auto = (capi.XP_TMA, capi.XP_TMA)
-        self._auto_fused = capi.XP_MULTIMEM if shards.world >= 4 else capi.XP_TMA
+        self._auto_fused = capi.XP_MULTIMEM if shards.world >= 8 else capi.XP_TMA
         self._buffers: List[SymBuffer] = []
         self._geoms = [capi.PeerGeom(shards.world, shards.rank, g, c) for g, _, c in shards.spans]
         self.geom = self._geoms[0]                          # (the only one unless the ShardGroup has parts > 1)
