@@ -106,8 +106,9 @@ def main():
             emit("fused_update_adamw_masked_clip", n, dtype, 25 + sg,
                  timer(lambda: hp.forget_step(p, g, max_norm=None)))
             emit("fused_update_adamw_ema", n, dtype, 32 + sg, timer(lambda: hp.remain_step(p, g, ema=True)))
-            if n <= hp.coop_max_elems:
+            if n <= 120_000_000:
                 # clipped forget step (norm + update): one cooperative launch vs memset + norm + scalar prep + update
+                hp.coop_max_elems, keep0 = 1 << 40, hp.coop_max_elems
                 emit("clipped_forget_step_one_cooperative_launch", n, dtype, 30 + 2 * sg,
                      timer(lambda: hp.forget_step(p, g, max_norm=1.0)),
                      note="sfr_clipped_update: zero + masked sum of squares + grid barrier + AdamW; g is read twice")
@@ -115,7 +116,7 @@ def main():
                 hp.coop_max_elems = 0
                 emit("clipped_forget_step_four_launches", n, dtype, 30 + 2 * sg,
                      timer(lambda: hp.forget_step(p, g, max_norm=1.0)))
-                hp.coop_max_elems = keep
+                hp.coop_max_elems = keep0
         if n <= 1_000_000_000:   # per-sample FIM, 4 rows (16 B/elem of gradient rows)
             n_pad = (n + 7) // 8 * 8          # row stride must keep every row 16-byte aligned
             rows = torch.empty(4, n_pad, device=dev).normal_(0, 1e-2, generator=gen)[:, :n]

@@ -820,9 +820,13 @@ template <int MODE>
 cudaError_t launch_apply_fused(int device, const float* a, const float* b, float eps, int64_t n,
                                const sfr_select_state* state, const unsigned long long* tie_base,
                                unsigned long long* scratch, uint8_t* mask, cudaStream_t s) {
+  // a grid-wide barrier costs more the more CTAs take part, and the phases between the barriers are short: one CTA
+  // per SM unless the vector is large enough to give every co-resident CTA some chunks
   const int64_t nchunks = (n + kChunk - 1) / kChunk;
-  int64_t want = nchunks > kMaxRegions * 4 ? nchunks : kMaxRegions * 4;
   const int cap = fused_grid<MODE>(device);
+  const int sms = device_geometry().sm_count;
+  int64_t want = nchunks / 32;
+  if (want < sms) want = sms;
   const int grid = (int)(want < cap ? want : cap);
   void* args[] = {(void*)&a, (void*)&b, (void*)&eps, (void*)&n, (void*)&state, (void*)&tie_base, (void*)&scratch,
                   (void*)&mask};

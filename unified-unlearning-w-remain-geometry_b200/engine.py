@@ -70,8 +70,12 @@ class HotPath:
         # device-side learning-rate schedule (set_lr_schedule): table of per-iteration rates + the iteration index
         self.lr_table: Optional[torch.Tensor] = None
         self.lr_index: Optional[torch.Tensor] = None
-        # clipped steps of vectors up to this size run as one cooperative launch (sfr_clipped_update)
-        self.coop_max_elems = 120_000_000
+        # clipped steps of vectors up to this size run as ONE cooperative launch (sfr_clipped_update).  Measured
+        # (profiles/r2_sweep_small.jsonl): on the device the one launch costs what the four stream-ordered launches cost
+        # at 1e7 elements (70.6 vs 68.6 us) and 5-7 % MORE at 3.9e7 / 1e8 (a persistent grid streams slower than one
+        # tile per CTA), so it is used where the saving is on the HOST side — three fewer launches per step in loops
+        # that are CPU-bound at this size (ResNet-18) — and nowhere else.
+        self.coop_max_elems = 20_000_000
         self.select_graphs = True
         self._select_graph_cache: Dict[tuple, object] = {}
         # a saliency mask exists only once it was BUILT (ratio_mask / topk_mask) or LOADED (set_buffer / load_mask):
