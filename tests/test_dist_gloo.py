@@ -58,6 +58,29 @@ def _shards_and_collectives(rank, tmp):
     assert torch.equal(p, want)
 
 
+def _spans_of_a_parted_vector(rank, tmp):
+    """ShardGroup(parts=P): every piece of the vector is split over the ranks; the spans of all ranks partition [0, n)
+    exactly, start on 16-element boundaries, and `local()` is their concatenation."""
+    from sfron_b200.dist import ShardGroup
+    n = 10_000 + 5
+    for parts in (2, 3, 4):
+        unit = 16 * WORLD * parts
+        n_pad = -(-n // unit) * unit
+        sg = ShardGroup(n, padded_len=n_pad, parts=parts)
+        assert len(sg.spans) == parts and all(g % 16 == 0 for g, _, c in sg.spans if c)
+        assert [off for _, off, _ in sg.spans] == [sum(c for _, _, c in sg.spans[:i]) for i in range(parts)]
+        mine = torch.zeros(n, dtype=torch.int32)
+        for g, _, c in sg.spans:
+            mine[g:g + c] += 1
+        dist.all_reduce(mine)
+        assert bool((mine == 1).all()), "spans of all ranks must cover every element exactly once"
+        full = torch.arange(n, dtype=torch.float32)
+        assert torch.equal(sg.local(full), torch.cat([full[g:g + c] for g, _, c in sg.spans]))
+        assert sg.local(full).numel() == sg.n_local
+        piece = n_pad // parts                                   # piece k starts at k * piece on every rank
+        assert all(k * piece <= g < (k + 1) * piece or c == 0 for k, (g, _, c) in enumerate(sg.spans))
+
+
 def _select_protocol(rank, tmp):
     from oracle import sfron_oracle as O
     from sfron_b200.dist import ShardGroup, scan_from_top, tie_bases
@@ -143,6 +166,10 @@ def _bucketed_gradient_exchange(rank, tmp):
         assert torch.equal(flat.g, want), step
         assert shard.data_ptr() == flat.g[sg.lo:].data_ptr() and shard.numel() == sg.n_local
     red.remove()
+
+
+def test_spans_of_a_parted_vector(tmp_path):
+    _spawn("_spans_of_a_parted_vector", tmp_path)
 
 
 def test_bucketed_gradient_exchange(tmp_path):
