@@ -288,7 +288,7 @@ STEP_MARKS = ["fisher_forget", "fisher_remain", "ratio_mask", "masked_sumsq", "f
               "fused_update_remain_ema"]
 
 
-def run_single(args, dev, hp_cls):
+def run_single(args, dev):
     """N = 1: the whole vector on one GPU (the configuration the metric is quoted on)."""
     import sfron_b200 as sfr
     n = args.elems
@@ -613,7 +613,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     sfr.capi.load()
-    r = run_single(args, dev, None) if world == 1 else run_dp(args, rank, world, dev)
+    r = run_single(args, dev) if world == 1 else run_dp(args, rank, world, dev)
     if rank != 0:
         return
     n = args.elems
