@@ -541,7 +541,7 @@ def run_dp(args, rank, world, dev):
         "transport": main_transport, "peer_error": peer_error,
         "what": "per step and per GPU: 2 gradient reduces (fused with K1) + 2 weight pushes (fused with K3), "
                 "7 cross-GPU barriers, the clip norm summed on one of them",
-        "nvlink_out_bytes_per_gpu": out_b, "nvlink_in_bytes_per_gpu": in_b,
+        "nvlink_out_bytes_per_gpu": out_b, "nvlink_in_bytes_per_gpu": in_b, "push_in_bytes_per_gpu": per_push_in,
         "link_GBps_per_direction": max(out_b, in_b) / (main["ms_per_step"] * 1e-3) / 1e9,
         "link_reference_GBps": 770.0,
         "note": "link rate over the WHOLE step (shard-local K2a / norm time included): a lower bound on the "
@@ -631,12 +631,21 @@ def run_ours(args, rank, world, local_rank):
                        frac=round(per_elem[k] * nl / (v * 1e-3) / 1e9 / peak, 4), bytes_per_elem=per_elem[k])
         kernels[k] = rec
     traffic, traffic_src = recorded_traffic(nl) if world == 1 else (None, "single-GPU capture only")
+    xk = {"tma": "fused_update_tma_kernel", "nccl": "fused_update_kernel"}.get(
+        (r["exchange"] or {}).get("transport", "").split("+")[-1], "fused_update_xchg_kernel")
     roofline = {"bound": "hbm", "kernel": "fused_update_kernel<AdamW,EMA_DIT,f32> (remain step + EMA)"
-                if world == 1 else "fused_update_xchg_kernel<AdamW,EMA_DIT> (remain step + EMA + weight push; "
-                "its HBM bytes on the shard — the kernel is NVLink-bound, see `exchange`)",
+                if world == 1 else f"{xk}<AdamW,EMA_DIT> (remain step + EMA + weight push; `achieved` = its HBM "
+                "bytes on the shard; the kernel is NVLink-bound: see `nvlink` below and `exchange`)",
                 "achieved": achieved, "peak": peak,
                 "peak_source": f"MEASURED_PEAKS.json ({peak_kind})" if peak_kind == "measured" else "fallback 6.65 TB/s",
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src}
+    if world > 1 and r["exchange"] and r["exchange"]["transport"] != "nccl":
+        # the same kernel against the link: bytes of the weight push this GPU must receive / its device time
+        push_in = r["exchange"]["push_in_bytes_per_gpu"]
+        link = push_in / (kernel_ms[dom] * 1e-3) / 1e9
+        roofline["nvlink"] = {"bound": "nvlink", "achieved": link, "peak": 770.0, "unit": "GB/s", "frac": link / 770.0,
+                              "peak_source": "peer-copy figure of B200_PROFILING.md (NCCL collectives reach 510-670 "
+                                             "GB/s bus bandwidth on these boxes)"}
     line = {
         "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": r["scaling"],

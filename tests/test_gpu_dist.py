@@ -116,11 +116,16 @@ def _nccl_exchange(rank, world, dev):
     for grads, step in ((gf, "forget"), (gr, "remain")):
         g = torch.zeros(n_pad, device=dev)
         g[:n].copy_(grads[rank])
-        whole = g.clone()
-        dist.all_reduce(whole, op=dist.ReduceOp.AVG)       # what the oracle is fed: the gradient AS reduced by NCCL
-        reduced.append(whole[:n].cpu())
         shard = sg.reduce_scatter_gradients_(g, average=True)
         assert shard.numel() == sg.n_local
+        # what the oracle is fed: the gradient AS reduce-scattered by NCCL (its summation order over 4+ ranks is not a
+        # sequential sum, nor the order of an all-reduce of the same data: last-bit differences that Adam amplifies
+        # where the mean gradient nearly cancels — a property of the collective, not of the sharded update)
+        pieces = [torch.zeros(sg.per, device=dev) for _ in range(world)]
+        mine = torch.zeros(sg.per, device=dev)
+        mine[:shard.numel()].copy_(shard)
+        dist.all_gather(pieces, mine)
+        reduced.append(torch.cat(pieces)[:n].cpu())
         if step == "forget":
             hp.forget_step(p[sg.lo:sg.hi], shard, max_norm=1.0)
         else:
@@ -246,7 +251,10 @@ def _bucketed_reducer(rank, world, dev):
     red.remove()
     model(x).pow(2).mean().backward()
     mono = sg.reduce_gradients_(flat.g, average=True)
-    assert torch.equal(shard, mono), "bucketed exchange != monolithic all-reduce"
+    if world == 2:
+        assert torch.equal(shard, mono), "bucketed exchange != monolithic all-reduce"
+    else:   # NCCL picks its algorithm (hence its summation order) by message size: last-bit differences beyond 2 ranks
+        assert torch.allclose(shard, mono, rtol=1e-5, atol=1e-7 * float(mono.abs().max())), "bucketed exchange != monolithic all-reduce"
 
 
 def _overlapped_backward(rank, world, dev):
