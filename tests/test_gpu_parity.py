@@ -281,6 +281,32 @@ def test_k2b_ties_lowest_index_first(sfr, dev, n):
         assert not bool(mask[x.isnan()].any())
 
 
+@pytest.mark.parametrize("prefix", [0, 1, 2, 0x007f, 0x0080, 0x3c23, 0x7f7f, 0x7f80])
+def test_k2b_values_on_prefix_boundaries(sfr, dev, prefix):
+    """Pass 1 tests key[30:16] against the chosen prefix with float compares on the value (select.cu hist1_tiles); the
+    bounds are the bit patterns (prefix << 16) - 1 and ((prefix + 1) << 16) - 1.  Values sitting exactly on, one below and
+    one above both bounds (subnormal bounds, FLT_MAX / inf at the top), with signs, zeros and NaN mixed in, and k swept so
+    that the threshold falls on each of them."""
+    g = gen(prefix + 3)
+    lo, hi = prefix << 16, (prefix + 1) << 16                      # keys of the bin: [lo, hi); key = bits + 1
+    bits = [b for b in (lo - 3, lo - 2, lo - 1, lo, lo + 1, (lo + hi) // 2, hi - 3, hi - 2, hi - 1, hi, hi + 1)
+            if 0 <= b <= 0x7f800000]
+    pool = torch.tensor(bits, dtype=torch.int32).view(torch.float32)
+    n = 40_003
+    x = pool[torch.randint(0, len(bits), (n,), generator=g)].clone()
+    x *= torch.where(torch.rand(n, generator=g) < 0.5, -1.0, 1.0)
+    x[torch.randint(0, n, (7,), generator=g)] = float("nan")
+    x[torch.randint(0, n, (9,), generator=g)] = 0.0
+    n_num = int((~x.isnan()).sum())
+    ks = {1, n_num}
+    for b in bits:                                                 # thresholds just before / inside / after each value's run
+        c = int((x.abs().view(torch.int32) >= b).logical_and(~x.isnan()).sum())
+        ks.update(k for k in (c - 1, c, c + 1) if 1 <= k <= n_num)
+    for k in sorted(ks):
+        mask, _ = run_topk(sfr, dev, x, k)
+        assert torch.equal(mask, O.topk_mask_flat(x, k)), (prefix, k)
+
+
 def test_k2b_all_equal_and_all_zero(sfr, dev):
     for val in (0.0, 2.5):
         x = torch.full((50_000,), val)

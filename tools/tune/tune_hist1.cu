@@ -121,6 +121,186 @@ hist1_b(const float4* __restrict__ a4, int64_t nvec, uint32_t prefix, u64* __res
   rc.flush(bins);
 }
 
+
+// ---- F: float-compare form (round 2): key tests as FSETP on |x|, keys built only for matching elements ------------------
+//   BINS / STAGE switch the two halves of the matching path off (to see what each costs);
+//   SLOW = 0: one branch per float4, elements handled one by one (product);  SLOW = 1: one warp-aggregated reservation per
+//   tile (ballot-free prefix sum over lanes with shuffles, ONE shared atomic per warp per tile);
+//   PREFETCH: the next tile's loads are issued before the current tile is processed (double buffer in registers).
+template <int LD>
+__device__ __forceinline__ float4 ld_var(const float4* p) {
+  if (LD == 0) return *p;
+  if (LD == 1) return __ldcs(p);
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+template <int THREADS, int UNROLL, int CTAS, bool BINS, bool STAGE, int SLOW, bool PREFETCH, int LD = 1>
+__global__ void __launch_bounds__(THREADS, CTAS)
+hist1_f(const float4* __restrict__ a4, int64_t nvec, uint32_t prefix, u64* __restrict__ bins, u64* __restrict__ regions,
+        u64 cap, u64* __restrict__ counts, unsigned int* __restrict__ m4) {
+  __shared__ unsigned int s_count;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  u64* region = regions + (u64)blockIdx.x * cap;
+  RunCache rc;
+  const float t_hi = __uint_as_float(((prefix + 1u) << 16) - 1u);
+  const float t_lo = __uint_as_float((prefix << 16) - 1u);
+  const int64_t tile = (int64_t)THREADS * UNROLL, ntiles = (nvec + tile - 1) / tile;
+  float4 x[UNROLL], nx[UNROLL];
+  auto load = [&](float4* dst, int64_t t) {
+    const int64_t base = t * tile + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t v = base + (int64_t)u * THREADS;
+      dst[u] = (t < ntiles && v < nvec) ? ld_var<LD>(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  if (PREFETCH) load(nx, blockIdx.x);
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    if (PREFETCH) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) x[u] = nx[u];
+      load(nx, t + gridDim.x);
+    } else {
+      load(x, t);
+    }
+    const int64_t base = t * tile + threadIdx.x;
+    uint32_t emask = 0;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t v = base + (int64_t)u * THREADS;
+      if (v >= nvec) continue;
+      const float r[4] = {fabsf(x[u].x), fabsf(x[u].y), fabsf(x[u].z), fabsf(x[u].w)};
+      bool g[4], e[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { g[q] = r[q] >= t_hi; e[q] = r[q] >= t_lo && !g[q]; }
+      m4[v] = (g[0] ? 1u : 0u) | (g[1] ? 0x100u : 0u) | (g[2] ? 0x10000u : 0u) | (g[3] ? 0x1000000u : 0u);
+      if (SLOW == 0) {
+        if (e[0] | e[1] | e[2] | e[3]) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (e[q]) {
+              const uint32_t k = __float_as_uint(r[q]) + 1u;
+              if (BINS) rc.push(bins, k & 0xffffu);
+              if (STAGE) {
+                const unsigned int pos = atomicAdd(&s_count, 1u);
+                if (pos < cap) region[pos] = ((u64)(v * 4 + q) << 16) | (k & 0xffffu);
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) emask |= (e[q] ? 1u : 0u) << (u * 4 + q);
+      }
+    }
+    if (SLOW == 1) {
+      if (__any_sync(0xffffffffu, emask != 0)) {
+        const unsigned int lane = threadIdx.x & 31u;
+        unsigned int mine = __popc(emask), incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned int o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
+        }
+        const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned int wbase = 0;
+        if (STAGE) {
+          if (lane == 31) wbase = atomicAdd(&s_count, total);
+          wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        }
+        unsigned int pos = wbase + incl - mine;
+        while (emask) {
+          const int j = __ffs(emask) - 1;
+          emask &= emask - 1;
+          const int u = j >> 2, q = j & 3;
+          const float4 xv = x[u & (UNROLL - 1)];
+          const float rv = fabsf(q == 0 ? xv.x : q == 1 ? xv.y : q == 2 ? xv.z : xv.w);
+          const uint32_t k = __float_as_uint(rv) + 1u;
+          if (BINS) atomicAdd(bins + (k & 0xffffu), 1ull);
+          if (STAGE) {
+            const int64_t v = base + (int64_t)u * THREADS;
+            if (pos < cap) region[pos] = ((u64)(v * 4 + q) << 16) | (k & 0xffffu);
+            ++pos;
+          }
+        }
+      }
+    }
+  }
+  if (BINS) rc.flush(bins);
+  __syncthreads();
+  if (threadIdx.x == 0) counts[blockIdx.x] = s_count;
+}
+
+
+// ---- L: large grid (the ratio-mask kernel's geometry), candidates collected in shared memory per CTA and appended to ONE
+// global list with one reservation per CTA; LD = 0 plain loads, 1 __ldcs (evict-first), 2 ld.global.nc.L1::no_allocate
+template <int THREADS, int UNROLL, int CTAS, int LD, bool STAGE, bool BLOCKED>
+__global__ void __launch_bounds__(THREADS, CTAS)
+hist1_l(const float4* __restrict__ a4, int64_t nvec, uint32_t prefix, u64* __restrict__ bins, u64* __restrict__ list,
+        u64 cap, u64* __restrict__ counts, unsigned int* __restrict__ m4) {
+  constexpr unsigned int SB = 256;
+  __shared__ u64 s_buf[SB];
+  __shared__ unsigned int s_count;
+  __shared__ u64 s_base;
+  if (STAGE) {
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+  }
+  RunCache rc;
+  const float t_hi = __uint_as_float(((prefix + 1u) << 16) - 1u);
+  const float t_lo = __uint_as_float((prefix << 16) - 1u);
+  const int64_t tile = (int64_t)THREADS * UNROLL, ntiles = (nvec + tile - 1) / tile;
+  const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t0 = BLOCKED ? blockIdx.x * per : blockIdx.x;
+  const int64_t t1 = BLOCKED ? (t0 + per < ntiles ? t0 + per : ntiles) : ntiles;
+  const int64_t dt = BLOCKED ? 1 : gridDim.x;
+  for (int64_t t = t0; t < t1; t += dt) {
+    const int64_t base = t * tile + threadIdx.x;
+    float4 x[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t v = base + (int64_t)u * THREADS;
+      x[u] = v < nvec ? ld_var<LD>(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t v = base + (int64_t)u * THREADS;
+      if (v >= nvec) continue;
+      const float r[4] = {fabsf(x[u].x), fabsf(x[u].y), fabsf(x[u].z), fabsf(x[u].w)};
+      bool g[4], e[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { g[q] = r[q] >= t_hi; e[q] = r[q] >= t_lo && !g[q]; }
+      m4[v] = (g[0] ? 1u : 0u) | (g[1] ? 0x100u : 0u) | (g[2] ? 0x10000u : 0u) | (g[3] ? 0x1000000u : 0u);
+      if (STAGE) {
+        if (e[0] | e[1] | e[2] | e[3]) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (e[q]) {
+              const uint32_t k = __float_as_uint(r[q]) + 1u;
+              rc.push(bins, k & 0xffffu);
+              const u64 entry = ((u64)(v * 4 + q) << 16) | (k & 0xffffu);
+              const unsigned int pos = atomicAdd(&s_count, 1u);
+              if (pos < SB) s_buf[pos] = entry;
+              else { const u64 gp = atomicAdd(counts, 1ull); if (gp < cap) list[gp] = entry; }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (STAGE) {
+    rc.flush(bins);
+    __syncthreads();
+    const unsigned int cnt = s_count < SB ? s_count : SB;
+    if (threadIdx.x == 0) s_base = cnt ? atomicAdd(counts, (u64)cnt) : 0ull;
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < cnt; i += THREADS)
+      if (s_base + i < cap) list[s_base + i] = s_buf[i];
+  }
+}
+
 __global__ void fill_normal(float* g, int64_t n, float sigma) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     uint64_t s = (uint64_t)i * 0x9E3779B97F4A7C15ull + 0x1234567ull;
@@ -262,5 +442,52 @@ int main() {
       hist1_b<256, 4, 6><<<grid, 256>>>(a4, nvec, prefix, bins, regions, total_cap / 192, counts, mask);
     });
   }
+
+#define RUN_F(NAME, TH, UN, CT, BINS, STAGE, SLOW, PF, ...)                                                        \
+  {                                                                                                            \
+    const int grid = sms * CT;                                                                                 \
+    run(NAME, grid, [&] {                                                                                      \
+      hist1_f<TH, UN, CT, BINS, STAGE, SLOW, PF, ##__VA_ARGS__><<<grid, TH>>>(a4, nvec, prefix, bins, regions, total_cap / grid, counts, mask); \
+    });                                                                                                        \
+  }
+  RUN_F("F  float compares, per-float4 branch (product r2), 256x4, 6/SM", 256, 4, 6, true, true, 0, false)
+  RUN_F("Z  float compares, mask only (no bins, no staging): ceiling", 256, 4, 6, false, false, 0, false)
+  RUN_F("Fb bins only", 256, 4, 6, true, false, 0, false)
+  RUN_F("Fs staging only", 256, 4, 6, false, true, 0, false)
+  RUN_F("G  per-tile warp-aggregated reservation, direct bin atomics", 256, 4, 6, true, true, 1, false)
+  RUN_F("P  F + register double buffer (prefetch), 256x4, 4/SM", 256, 4, 4, true, true, 0, true)
+  RUN_F("P2 F + prefetch, 256x2, 6/SM", 256, 2, 6, true, true, 0, true)
+  RUN_F("GP G + prefetch, 256x4, 4/SM", 256, 4, 4, true, true, 1, true)
+  RUN_F("ZP Z + prefetch, 256x4, 4/SM", 256, 4, 4, false, false, 0, true)
+  RUN_F("Z8 Z, 128x4, 12/SM", 128, 4, 12, false, false, 0, false)
+  RUN_F("F8 F, 256x8, 3/SM", 256, 8, 3, true, true, 0, false)
+  RUN_F("Fp F with PLAIN loads, 256x4, 6/SM", 256, 4, 6, true, true, 0, false, 0)
+  RUN_F("Zp Z with PLAIN loads, 256x4, 6/SM", 256, 4, 6, false, false, 0, false, 0)
+  RUN_F("Pp P with PLAIN loads, 256x4, 4/SM", 256, 4, 4, true, true, 0, true, 0)
+  RUN_F("Fp2 F PLAIN, 128x4, 12/SM", 128, 4, 12, true, true, 0, false, 0)
+  RUN_F("Fp3 F PLAIN, 128x2, 16/SM", 128, 2, 16, true, true, 0, false, 0)
+  RUN_F("Fp4 F PLAIN, 256x8, 3/SM", 256, 8, 3, true, true, 0, false, 0)
+#define RUN_L(NAME, TH, UN, CT, LD, STAGE, BLOCKED, TPC)                                                      \
+  {                                                                                                            \
+    const int64_t tiles = (nvec + (int64_t)TH * UN - 1) / ((int64_t)TH * UN);                                  \
+    int64_t g64 = tiles / TPC;                                                                                 \
+    if (g64 > (int64_t)sms * 512) g64 = (int64_t)sms * 512;                                                    \
+    const int grid = (int)g64;                                                                                 \
+    run(NAME, grid, [&] {                                                                                      \
+      hist1_l<TH, UN, CT, LD, STAGE, BLOCKED><<<grid, TH>>>(a4, nvec, prefix, bins, regions, total_cap, counts, mask); \
+    });                                                                                                        \
+  }
+  RUN_L("ZL0 mask only, 128x2, large grid (>= 8 tiles/CTA), plain loads", 128, 2, 8, 0, false, false, 8)
+  RUN_L("ZL1 mask only, 128x2, large grid, __ldcs", 128, 2, 8, 1, false, false, 8)
+  RUN_L("ZL2 mask only, 128x2, large grid, ld.nc.no_allocate", 128, 2, 8, 2, false, false, 8)
+  RUN_L("ZL3 mask only, 128x4, large grid, plain", 128, 4, 8, 0, false, false, 8)
+  RUN_L("ZL4 mask only, 256x2, large grid, plain", 256, 2, 4, 0, false, false, 8)
+  RUN_L("ZL5 mask only, 128x2, large grid, plain, BLOCKED tile ranges", 128, 2, 8, 0, false, true, 8)
+  RUN_L("ZL6 mask only, 128x2, one tile per CTA, plain", 128, 2, 8, 0, false, false, 1)
+  RUN_L("L0  staged (smem list, one reservation per CTA), 128x2, large grid, plain", 128, 2, 8, 0, true, false, 8)
+  RUN_L("L1  staged, 128x2, large grid, __ldcs", 128, 2, 8, 1, true, false, 8)
+  RUN_L("L3  staged, 128x4, large grid, plain", 128, 4, 8, 0, true, false, 8)
+  RUN_L("L5  staged, 128x2, large grid, plain, BLOCKED", 128, 2, 8, 0, true, true, 8)
+  RUN_L("L6  staged, 128x2, 32 tiles per CTA, plain", 128, 2, 8, 0, true, false, 32)
   return 0;
 }

@@ -80,9 +80,10 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // ---- vector access ---------------------------------------------------------------
 // ld_stream / st_stream: streams of read-modify-write kernels (default caching).
-// ld_once: data a kernel reads exactly once and never writes (evict-first).
-__device__ __forceinline__ float4 ld_once(const float4* p) { return __ldcs(p); }
-__device__ __forceinline__ float ld_once(const float* p) { return __ldcs(p); }
+// ld_once: data a read-mostly kernel (the select passes) reads exactly once and never writes.  Default caching: on B200 the
+// evict-first hint (__ldcs) costs these kernels 7 % (tools/tune/tune_hist1.cu, ZL0 / ZL1 and Z / Zp: 6.96 vs 6.46 TB/s).
+__device__ __forceinline__ float4 ld_once(const float4* p) { return *p; }
+__device__ __forceinline__ float ld_once(const float* p) { return *p; }
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return *p; }
 __device__ __forceinline__ void st_stream(float4* p, float4 v) { *p = v; }
 __device__ __forceinline__ float ld_stream(const float* p) { return *p; }
@@ -130,12 +131,14 @@ __device__ __forceinline__ void zero_g1(void* g, int64_t i) {
   }
 }
 
+// Gradient and mask words are read once per kernel, with DEFAULT caching: an A/B at N3 of the whole library built with
+// __ldcs here instead (profiles/r2_ab_load_hint.jsonl) has the clip norm 4.7 % slower and everything else within noise.
 template <int GT>
 __device__ __forceinline__ float4 load_g4_once(const void* g, int64_t vec) {
   if constexpr (GT == SFR_F32) {
-    return __ldcs(reinterpret_cast<const float4*>(g) + vec);
+    return *(reinterpret_cast<const float4*>(g) + vec);
   } else {
-    uint2 raw = __ldcs(reinterpret_cast<const uint2*>(g) + vec);
+    uint2 raw = *(reinterpret_cast<const uint2*>(g) + vec);
     float4 r;
     r.x = bf16_bits_to_f32(raw.x & 0xffffu);
     r.y = bf16_bits_to_f32(raw.x >> 16);
@@ -145,7 +148,7 @@ __device__ __forceinline__ float4 load_g4_once(const void* g, int64_t vec) {
   }
 }
 __device__ __forceinline__ uint32_t load_mask4_once(const uint8_t* mask, int64_t vec) {
-  return __ldcs(reinterpret_cast<const unsigned int*>(mask) + vec);
+  return *(reinterpret_cast<const unsigned int*>(mask) + vec);
 }
 
 // Four mask bytes (0/1) for elements 4*vec .. 4*vec+3.

@@ -31,15 +31,21 @@ namespace {
 namespace cg = cooperative_groups;
 
 // ---- key source ------------------------------------------------------------------------
+// The float whose magnitude is ranked.
+template <int MODE>
+__device__ __forceinline__ float key_value(float a, float b, float eps) {
+  if constexpr (MODE == SFR_KEY_ABS) {
+    return a;
+  } else if constexpr (MODE == SFR_KEY_RATIO) {
+    return __fdiv_rn(__fadd_rn(a, eps), __fadd_rn(b, eps));
+  } else {  // SFR_KEY_ABSDIFF: |a - b|  (proximal_gradient.py:158-159: params -= init ; abs_())
+    return __fsub_rn(a, b);
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ uint32_t key_from(float a, float b, float eps) {
-  if constexpr (MODE == SFR_KEY_ABS) {
-    return select_key(a);
-  } else if constexpr (MODE == SFR_KEY_RATIO) {
-    return select_key(__fdiv_rn(__fadd_rn(a, eps), __fadd_rn(b, eps)));
-  } else {  // SFR_KEY_ABSDIFF: |a - b|  (proximal_gradient.py:158-159: params -= init ; abs_())
-    return select_key(__fsub_rn(a, b));
-  }
+  return select_key(key_value<MODE>(a, b, eps));
 }
 
 // Per-thread run-length cache in front of the GLOBAL-memory histogram of pass 1: consecutive items of
@@ -149,7 +155,7 @@ __host__ __device__ inline int64_t scratch_cand_cap(int64_t n) {
 // from this short list instead of re-reading the whole vector; if any region overflows (degenerate
 // inputs: most keys equal) a flag makes the apply fall back to the streaming count.
 constexpr int kFiltThreads = 256;
-constexpr int kFiltCtasPerSm = 6;
+constexpr int kFiltCtasPerSm = 4;     // 64 registers per thread: room for the double buffer
 constexpr int kFiltUnroll = 4;
 
 struct CandStage {
@@ -164,6 +170,88 @@ struct CandStage {
     else *reinterpret_cast<volatile unsigned int*>(s_over) = 1u;
   }
 };
+
+// The vectorised body of pass 1.  A key is  bits(|x|) + 1  (0 for NaN), so on non-negative floats key order IS float order
+// and both tests of the hot loop are one FSETP on the value itself, with no key arithmetic:
+//     key[30:16] >  prefix   <=>   |x| >= as_float(((prefix + 1) << 16) - 1)
+//     key[30:16] == prefix   <=>   |x| >= as_float((prefix << 16) - 1)  and not the above          (prefix >= 1)
+// (NaN fails every ordered compare, as its key 0 fails both tests; a bound that is itself a NaN pattern — prefix at the top
+// of the range — makes its test false for every value, which is also what the keys say.  Compares are IEEE: the library is
+// built without flush-to-zero, so the subnormal bounds of small prefixes order correctly.)  prefix == 0 — the threshold
+// sits among zeros / subnormals, and NaN keys belong to the bin — takes the integer form (FAST = false).  Keys are built
+// only for the few elements that match the prefix; one branch per float4 guards that path.
+template <int MODE, bool WRITE, bool FAST>
+__device__ __forceinline__ void hist1_tiles(const float* __restrict__ a, const float* __restrict__ b, float eps,
+                                            int64_t nvec, uint32_t prefix, unsigned long long* __restrict__ bins,
+                                            uint8_t* __restrict__ mask, RunCache<unsigned long long>& rc, CandStage& cs) {
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  const float t_hi = __uint_as_float(((prefix + 1u) << 16) - 1u);
+  const float t_lo = __uint_as_float((prefix << 16) - 1u);
+
+  // Register double buffer: the loads of this CTA's NEXT tile are in flight while the current one is tested, so the
+  // bytes outstanding per SM never drop to zero between tiles (tools/tune/tune_hist1.cu, variants F / P: +7 %).
+  constexpr int U = MODE == SFR_KEY_ABS ? kFiltUnroll : kFiltUnroll / 2;   // two inputs: half the tile, same bytes in flight
+  const int64_t tile = (int64_t)kFiltThreads * U;
+  const int64_t ntiles = (nvec + tile - 1) / tile;
+  float4 x[U], y[U], nx[U], ny[U];
+  auto load_tile = [&](float4* dx, float4* dy, int64_t t) {
+    const int64_t base = t * tile + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = base + (int64_t)u * kFiltThreads;
+      const bool in = t < ntiles && v < nvec;
+      dx[u] = in ? ld_once(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (MODE != SFR_KEY_ABS)
+        dy[u] = in ? ld_once(b4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      else
+        dy[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  load_tile(nx, ny, blockIdx.x);
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * tile + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      x[u] = nx[u];
+      y[u] = ny[u];
+    }
+    load_tile(nx, ny, t + gridDim.x);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = base + (int64_t)u * kFiltThreads;
+      if (v >= nvec) continue;
+      if constexpr (FAST) {
+        const float r0 = fabsf(key_value<MODE>(x[u].x, y[u].x, eps)), r1 = fabsf(key_value<MODE>(x[u].y, y[u].y, eps));
+        const float r2 = fabsf(key_value<MODE>(x[u].z, y[u].z, eps)), r3 = fabsf(key_value<MODE>(x[u].w, y[u].w, eps));
+        const bool g0 = r0 >= t_hi, g1 = r1 >= t_hi, g2 = r2 >= t_hi, g3 = r3 >= t_hi;
+        const bool e0 = r0 >= t_lo && !g0, e1 = r1 >= t_lo && !g1, e2 = r2 >= t_lo && !g2, e3 = r3 >= t_lo && !g3;
+        if constexpr (WRITE)
+          reinterpret_cast<unsigned int*>(mask)[v] = (g0 ? 1u : 0u) | (g1 ? 0x100u : 0u) | (g2 ? 0x10000u : 0u) | (g3 ? 0x1000000u : 0u);
+        if (e0 | e1 | e2 | e3) {     // a matching value is finite or +inf, never NaN: its key is bits + 1
+          if (e0) { const uint32_t k = __float_as_uint(r0) + 1u; rc.push(bins, k & 0xffffu); cs.push(v * 4 + 0, k); }
+          if (e1) { const uint32_t k = __float_as_uint(r1) + 1u; rc.push(bins, k & 0xffffu); cs.push(v * 4 + 1, k); }
+          if (e2) { const uint32_t k = __float_as_uint(r2) + 1u; rc.push(bins, k & 0xffffu); cs.push(v * 4 + 2, k); }
+          if (e3) { const uint32_t k = __float_as_uint(r3) + 1u; rc.push(bins, k & 0xffffu); cs.push(v * 4 + 3, k); }
+        }
+      } else {
+        const uint32_t k0 = key_from<MODE>(x[u].x, y[u].x, eps);
+        const uint32_t k1 = key_from<MODE>(x[u].y, y[u].y, eps);
+        const uint32_t k2 = key_from<MODE>(x[u].z, y[u].z, eps);
+        const uint32_t k3 = key_from<MODE>(x[u].w, y[u].w, eps);
+        if ((k0 >> 16) == prefix) { rc.push(bins, k0 & 0xffffu); cs.push(v * 4 + 0, k0); }
+        if ((k1 >> 16) == prefix) { rc.push(bins, k1 & 0xffffu); cs.push(v * 4 + 1, k1); }
+        if ((k2 >> 16) == prefix) { rc.push(bins, k2 & 0xffffu); cs.push(v * 4 + 2, k2); }
+        if ((k3 >> 16) == prefix) { rc.push(bins, k3 & 0xffffu); cs.push(v * 4 + 3, k3); }
+        if constexpr (WRITE) {
+          const uint32_t s0 = (k0 >> 16) > prefix, s1 = (k1 >> 16) > prefix;
+          const uint32_t s2 = (k2 >> 16) > prefix, s3 = (k3 >> 16) > prefix;
+          reinterpret_cast<unsigned int*>(mask)[v] = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+        }
+      }
+    }
+  }
+}
 
 // With WRITE the pass also leaves a PROVISIONAL mask: 1 where key[30:16] > prefix, 0 elsewhere — final
 // for every element except the staged ones, which sfr_select_apply then resolves from the candidate
@@ -190,44 +278,11 @@ select_hist1_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
 
   const uint32_t prefix = state->prefix;
   const int64_t nvec = n >> 2;
-  const int64_t tile = (int64_t)kFiltThreads * kFiltUnroll;
-  const int64_t ntiles = (nvec + tile - 1) / tile;
-  const float4* a4 = reinterpret_cast<const float4*>(a);
-  const float4* b4 = reinterpret_cast<const float4*>(b);
   RunCache<unsigned long long> rc;
-
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t base = t * tile + threadIdx.x;
-    float4 x[kFiltUnroll], y[kFiltUnroll];
-#pragma unroll
-    for (int u = 0; u < kFiltUnroll; ++u) {
-      const int64_t v = base + (int64_t)u * kFiltThreads;
-      const bool in = v < nvec;
-      x[u] = in ? ld_once(a4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if constexpr (MODE != SFR_KEY_ABS)
-        y[u] = in ? ld_once(b4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-      else
-        y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < kFiltUnroll; ++u) {
-      const int64_t v = base + (int64_t)u * kFiltThreads;
-      if (v >= nvec) continue;
-      const uint32_t k0 = key_from<MODE>(x[u].x, y[u].x, eps);
-      const uint32_t k1 = key_from<MODE>(x[u].y, y[u].y, eps);
-      const uint32_t k2 = key_from<MODE>(x[u].z, y[u].z, eps);
-      const uint32_t k3 = key_from<MODE>(x[u].w, y[u].w, eps);
-      if ((k0 >> 16) == prefix) { rc.push(bins, k0 & 0xffffu); cs.push(v * 4 + 0, k0); }
-      if ((k1 >> 16) == prefix) { rc.push(bins, k1 & 0xffffu); cs.push(v * 4 + 1, k1); }
-      if ((k2 >> 16) == prefix) { rc.push(bins, k2 & 0xffffu); cs.push(v * 4 + 2, k2); }
-      if ((k3 >> 16) == prefix) { rc.push(bins, k3 & 0xffffu); cs.push(v * 4 + 3, k3); }
-      if constexpr (WRITE) {
-        const uint32_t s0 = (k0 >> 16) > prefix, s1 = (k1 >> 16) > prefix;
-        const uint32_t s2 = (k2 >> 16) > prefix, s3 = (k3 >> 16) > prefix;
-        reinterpret_cast<unsigned int*>(mask)[v] = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
-      }
-    }
-  }
+  if (prefix != 0u)
+    hist1_tiles<MODE, WRITE, true>(a, b, eps, nvec, prefix, bins, mask, rc, cs);
+  else
+    hist1_tiles<MODE, WRITE, false>(a, b, eps, nvec, prefix, bins, mask, rc, cs);
   const int64_t tail0 = nvec << 2;
   if (blockIdx.x == 0 && threadIdx.x < (n - tail0)) {
     const int64_t i = tail0 + threadIdx.x;
