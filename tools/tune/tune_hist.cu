@@ -44,6 +44,37 @@ __global__ void __launch_bounds__(THREADS, 1) hist(const float* __restrict__ a, 
   __syncthreads();
   for (int i = threadIdx.x; i < NB; i += THREADS) { unsigned int c = 0; for (int k = 0; k < COPIES; ++k) c += h[k * NB + i]; if (c) atomicAdd(bins + i, (unsigned long long)c); }
 }
+
+// ---- round 2: load hint and register double buffer for the product form (plain shared atomics, 15 bits, 1024 threads) ----
+template <int THREADS, int UNROLL, bool PLAIN, bool PREFETCH>
+__global__ void __launch_bounds__(THREADS, 1) hist_p(const float* __restrict__ a, int64_t n, unsigned long long* __restrict__ bins) {
+  extern __shared__ unsigned int h[];
+  constexpr int NB = 1 << 15;
+  for (int i = threadIdx.x; i < NB; i += THREADS) h[i] = 0;
+  __syncthreads();
+  const int64_t nvec = n >> 2, tile = (int64_t)THREADS * UNROLL, ntiles = (nvec + tile - 1) / tile;
+  const float4* a4 = (const float4*)a;
+  float4 x[UNROLL], nx[UNROLL];
+  auto load = [&](float4* d, int64_t t) {
+    const int64_t base = t * tile + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) { int64_t v = base + (int64_t)u * THREADS; d[u] = (t < ntiles && v < nvec) ? (PLAIN ? a4[v] : __ldcs(a4 + v)) : make_float4(0, 0, 0, 0); }
+  };
+  if (PREFETCH) load(nx, blockIdx.x);
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    if (PREFETCH) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) x[u] = nx[u];
+      load(nx, t + gridDim.x);
+    } else load(x, t);
+    const int64_t base = t * tile + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) { int64_t v = base + (int64_t)u * THREADS; if (v < nvec) {
+      atomicAdd(h + (key_of(x[u].x) >> 16), 1u); atomicAdd(h + (key_of(x[u].y) >> 16), 1u); atomicAdd(h + (key_of(x[u].z) >> 16), 1u); atomicAdd(h + (key_of(x[u].w) >> 16), 1u); } }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NB; i += THREADS) { unsigned int c = h[i]; if (c) atomicAdd(bins + i, (unsigned long long)c); }
+}
 static char* flushbuf;
 template <typename F> float timeit(F f) { std::vector<float> t; cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   for (int i = 0; i < 7; ++i) { cudaMemsetAsync(flushbuf, i, 256 << 20); cudaEventRecord(a); f(); cudaEventRecord(b); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms, a, b); if (i >= 2) t.push_back(ms); }
@@ -58,6 +89,10 @@ int main() {
     if (pass == 1) { cudaMemset(g, 0, n * 4); printf("--- all zeros\n"); }
     if (pass == 2) { fill<<<148 * 8, 256>>>(g, n, 99); cudaDeviceSynchronize(); cudaMemset(g, 0, (n / 10 * 9) * 4); printf("--- 90%% zeros then gaussian\n"); }
     RUN(15, 1, 1024, 4, 0, 1) RUN(15, 1, 1024, 4, 1, 1) RUN(15, 1, 1024, 4, 2, 1) RUN(15, 1, 1024, 4, 3, 1)
+#define RUNP(T, U, PL, PF) { int smem = (1 << 15) * 4; cudaFuncSetAttribute(hist_p<T, U, PL, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    float ms = timeit([&] { cudaMemsetAsync(bins, 0, 8 << 20); hist_p<T, U, PL, PF><<<148, T, smem>>>(g, n, bins); }); \
+    cudaError_t e = cudaGetLastError(); printf("hist_p threads=%d unroll=%d plain=%d prefetch=%d  %.4f ms  %.1f GB/s %s\n", T, U, (int)PL, (int)PF, ms, 4.0 * n / ms / 1e6, e == cudaSuccess ? "" : cudaGetErrorString(e)); }
+    RUNP(1024, 4, false, false) RUNP(1024, 4, true, false) RUNP(1024, 4, true, true) RUNP(1024, 2, true, true) RUNP(1024, 8, true, false) RUNP(512, 4, true, true) RUNP(512, 8, true, true)
   }
   return 0;
 }
