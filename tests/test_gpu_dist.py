@@ -142,7 +142,6 @@ def _nccl_exchange(rank, world, dev):
 def _peer_exchange(rank, world, dev):
     import torch.distributed as dist
     import sfron_b200 as sfr
-    from sfron_b200 import capi
     from sfron_b200.dist import PeerExchange, ShardGroup, ShardedHotPath
     from oracle import sfron_oracle as O
     n = 1_000_003

@@ -37,7 +37,6 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     import sfron_b200 as sfr
-    from sfron_b200 import capi
     from sfron_b200.dist import PeerExchange, ShardGroup, ShardedHotPath
 
     n = args.elems
