@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <vector>
+#include <string>
 #include <algorithm>
 
 enum Hint { CS = 0, NC = 1, PLAIN = 2 };
@@ -83,6 +84,42 @@ __global__ void __launch_bounds__(THREADS, CTAS) ka(const float* __restrict__ g,
   }
 }
 
+
+// ---- round 2: K3 masked AdamW with bf16 gradients — 4 elements per thread (8-byte gradient loads: product) vs 8 (16-byte);
+// GB = 0: fp32 gradient (29 B/elem); 1: bf16 gradient, 4 per thread; 2: bf16 gradient, 8 per thread (27 B/elem)
+__device__ __forceinline__ float bf(uint32_t b) { return __uint_as_float(b << 16); }
+#define UPDM(P, M, V, gg, mk) { float g_ = (gg) * (mk); M = fmaf(g_ - M, 0.1f, M); V = fmaf(0.001f * g_, g_, V * 0.999f); P = P + (-1e-4f * M) / (sqrtf(V) / 0.03f + 1e-8f); }
+template <int THREADS, int CTAS, int GB>
+__global__ void __launch_bounds__(THREADS, CTAS) k3m(float* __restrict__ p, const void* __restrict__ g, const unsigned char* __restrict__ mask,
+                                                      float* __restrict__ m, float* __restrict__ v, int64_t n) {
+  float4 *p4 = (float4*)p, *m4 = (float4*)m, *v4 = (float4*)v;
+  if (GB < 2) {
+    const int64_t nvec = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * THREADS) {
+      float4 G;
+      if (GB == 0) G = ((const float4*)g)[i];
+      else { uint2 r = ((const uint2*)g)[i]; G = make_float4(bf(r.x & 0xffffu), bf(r.x >> 16), bf(r.y & 0xffffu), bf(r.y >> 16)); }
+      const uint32_t mk = ((const uint32_t*)mask)[i];
+      float4 P = p4[i], M = m4[i], V = v4[i];
+      UPDM(P.x, M.x, V.x, G.x, (float)(mk & 0xffu)) UPDM(P.y, M.y, V.y, G.y, (float)((mk >> 8) & 0xffu))
+      UPDM(P.z, M.z, V.z, G.z, (float)((mk >> 16) & 0xffu)) UPDM(P.w, M.w, V.w, G.w, (float)(mk >> 24))
+      p4[i] = P; m4[i] = M; v4[i] = V;
+    }
+  } else {
+    const int64_t n8 = n >> 3;
+    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n8; i += (int64_t)gridDim.x * THREADS) {
+      const uint4 r = ((const uint4*)g)[i];
+      const uint2 mk = ((const uint2*)mask)[i];
+      float4 P0 = p4[2 * i], P1 = p4[2 * i + 1], M0 = m4[2 * i], M1 = m4[2 * i + 1], V0 = v4[2 * i], V1 = v4[2 * i + 1];
+      UPDM(P0.x, M0.x, V0.x, bf(r.x & 0xffffu), (float)(mk.x & 0xffu)) UPDM(P0.y, M0.y, V0.y, bf(r.x >> 16), (float)((mk.x >> 8) & 0xffu))
+      UPDM(P0.z, M0.z, V0.z, bf(r.y & 0xffffu), (float)((mk.x >> 16) & 0xffu)) UPDM(P0.w, M0.w, V0.w, bf(r.y >> 16), (float)(mk.x >> 24))
+      UPDM(P1.x, M1.x, V1.x, bf(r.z & 0xffffu), (float)(mk.y & 0xffu)) UPDM(P1.y, M1.y, V1.y, bf(r.z >> 16), (float)((mk.y >> 8) & 0xffu))
+      UPDM(P1.z, M1.z, V1.z, bf(r.w & 0xffffu), (float)((mk.y >> 16) & 0xffu)) UPDM(P1.w, M1.w, V1.w, bf(r.w >> 16), (float)(mk.y >> 24))
+      p4[2 * i] = P0; p4[2 * i + 1] = P1; m4[2 * i] = M0; m4[2 * i + 1] = M1; v4[2 * i] = V0; v4[2 * i + 1] = V1;
+    }
+  }
+}
+
 static float* dalloc(int64_t n) { float* p; cudaMalloc(&p, n * 4); cudaMemset(p, 0, n * 4); return p; }
 static char* flushbuf; 
 template <typename F> float timeit(F f) {
@@ -91,14 +128,22 @@ template <typename F> float timeit(F f) {
   std::sort(t.begin(), t.end()); return t[t.size() / 2];
 }
 
-int main() {
+int main(int argc, char** argv) {
   const int64_t n = 675129632, nvec = n / 4; const int sms = 148;
+  const bool only_k3m = argc > 1 && std::string(argv[1]) == "k3m";   // round-2 experiment alone
   float *p = dalloc(n), *g = dalloc(n), *m = dalloc(n), *v = dalloc(n), *e = dalloc(n);
   cudaMalloc(&flushbuf, 256 << 20);
 #define RUN1(T, U, C, H, MULT) { int64_t gg = (int64_t)sms * C * MULT, nt = (nvec + (int64_t)T * U - 1) / ((int64_t)T * U); int grid = (int)(gg < nt ? gg : nt); float ms = timeit([&] { k1<T, U, C, H><<<grid, T>>>(p, g, nvec, 2000.f); }); \
     printf("k1 threads=%d unroll=%d ctas=%d hint=%d gridmult=%d  %.4f ms  %.1f GB/s\n", T, U, C, H, MULT, ms, 12.0 * n / ms / 1e6); }
 #define RUN3(T, U, C, H, MULT) { int64_t gg = (int64_t)sms * C * MULT, nt = (nvec + (int64_t)T * U - 1) / ((int64_t)T * U); int grid = (int)(gg < nt ? gg : nt); float ms = timeit([&] { k3<T, U, C, H><<<grid, T>>>(p, g, m, v, e, nvec); }); \
     printf("k3 threads=%d unroll=%d ctas=%d hint=%d gridmult=%d  %.4f ms  %.1f GB/s\n", T, U, C, H, MULT, ms, 36.0 * n / ms / 1e6); }
+
+#define RUN3M(T, C, GB, MULT) { const int64_t items = GB == 2 ? n / 8 : n / 4; int64_t gg = (int64_t)sms * C * MULT, nt = (items + T - 1) / T; int grid = (int)(gg < nt ? gg : nt); \
+    float ms = timeit([&] { k3m<T, C, GB><<<grid, T>>>(p, g, (const unsigned char*)e, m, v, n); }); \
+    printf("k3m threads=%d ctas=%d gradient=%s gridmult=%d  %.4f ms  %.1f GB/s\n", T, C, GB == 0 ? "f32" : GB == 1 ? "bf16x4" : "bf16x8", MULT, ms, (GB == 0 ? 29.0 : 27.0) * n / ms / 1e6); }
+  cudaMemset(e, 1, n);
+  RUN3M(128, 6, 0, 100000) RUN3M(128, 6, 1, 100000) RUN3M(128, 6, 2, 100000) RUN3M(128, 4, 2, 100000) RUN3M(256, 3, 2, 100000) RUN3M(128, 6, 2, 32) RUN3M(128, 6, 1, 32) RUN3M(64, 12, 2, 100000)
+  if (only_k3m) return 0;
   unsigned* outp; cudaMalloc(&outp, 64);
 #define RUNR(T, U, C, H, MULT) { int64_t gg = (int64_t)sms * C * MULT, nt = (nvec + (int64_t)T * U - 1) / ((int64_t)T * U); int grid = (int)(gg < nt ? gg : nt); float ms = timeit([&] { kr<T, U, C, H><<<grid, T>>>(g, nvec, outp); }); \
     printf("kr threads=%d unroll=%d ctas=%d hint=%d gridmult=%d  %.4f ms  %.1f GB/s\n", T, U, C, H, MULT, ms, 4.0 * n / ms / 1e6); }
