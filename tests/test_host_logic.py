@@ -170,3 +170,41 @@ def test_format_converters_single_copy_semantics(tmp_path):
         m = to_dict(layout, bits)
         assert all(t.dtype == dtype for t in m.values())
         assert torch.equal(formats.load_mask(m, layout), bits)
+
+
+def test_cli_flags_match_the_reference():
+    """The drop-in command lines accept the reference scripts' flags with the same defaults, types, `required`, `nargs`
+    and store_true actions.  The fixture was read statically from the reference's sources
+    (tests/golden/make_cli_flags.py); the one deliberate difference is listed here."""
+    import argparse
+    import json
+    import os
+    from sfron_b200.methods import dit, masks, sd
+    doc = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cli_flags.json")))
+    sub = {a.dest: a for a in masks.build_parser()._actions}["family"].choices
+    ours = {"dit_forget": dit.forget_parser(), "dit_generate_fisher": dit.generate_fisher_parser(),
+            "dit_generate_mask": sub["dit"], "sd_generate_fisher": sd.generate_fisher_parser(),
+            "sd_nsfw_removal": sd.nsfw_removal_parser(), "sd_generate_fisher_mask": sub["sd"],
+            "ddpm_generate_fisher_mask": sub["ddpm"]}
+    # SD/train-scripts/nsfw_removal.py declares --lr with type=int (any `--lr 1e-5` on its command line fails to parse);
+    # the default is the float 1e-5 and the value feeds Adam's lr, so the flag is a float here
+    deliberate = {("sd_nsfw_removal", "--lr", "type")}
+    assert set(ours) == set(doc)
+    for name, parser in ours.items():
+        mine = {a.option_strings[0]: a for a in parser._actions if a.option_strings and a.dest != "help"}
+        theirs = {f["flags"][0]: f for f in doc[name]["flags"]}
+        assert set(mine) == set(theirs), (name, set(mine) ^ set(theirs))
+        for flag, ref in theirs.items():
+            a = mine[flag]
+            assert list(a.option_strings) == ref["flags"], (name, flag)
+            if ref.get("action") == "store_true":
+                assert isinstance(a, argparse._StoreTrueAction), (name, flag)
+                continue
+            if (name, flag, "type") not in deliberate:
+                assert (a.type.__name__ if a.type else None) == ref.get("type"), (name, flag, "type")
+            if not (isinstance(ref.get("default"), str) and ref["default"].startswith("<expr>")):
+                assert a.default == ref.get("default"), (name, flag, "default", a.default)
+            assert bool(a.required) == bool(ref.get("required", False)), (name, flag, "required")
+            assert a.nargs == ref.get("nargs"), (name, flag, "nargs")
+            if isinstance(ref.get("choices"), list):
+                assert list(a.choices) == ref["choices"], (name, flag, "choices")

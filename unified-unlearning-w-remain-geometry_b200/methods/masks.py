@@ -76,7 +76,9 @@ def generate_mask_dit(mask_path: str, forget_class: Sequence[int], thresholds: S
     return written
 
 
-def main(argv=None):
+def build_parser() -> argparse.ArgumentParser:
+    """One sub-command per family, each with the flags of the reference script it stands for:
+    DDPM/generate_fisher_mask.py:17-24, SD/train-scripts/generate_fisher_mask.py:17-24, DiT/generate_mask.py:50-56."""
     ap = argparse.ArgumentParser(prog="sfron_b200.methods.masks")
     sub = ap.add_subparsers(dest="family", required=True)
     for fam in ("ddpm", "sd"):
@@ -87,7 +89,11 @@ def main(argv=None):
     p.add_argument("--mask-path", required=True, type=str, default="./mask")
     p.add_argument("--forget-class", nargs="+", type=int, required=True)
     p.add_argument("--thresholds", nargs="+", type=float, default=[0.5, 1, 3, 5, 10])
-    args = ap.parse_args(argv)
+    return ap
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
     if args.family == "ddpm":
         generate_fisher_mask(args.ckpt_folder, args.threshold)
     elif args.family == "sd":

@@ -189,13 +189,13 @@ def generate_fisher_parser() -> argparse.ArgumentParser:
     """SD/train-scripts/generate_fisher.py:133-203."""
     p = argparse.ArgumentParser(prog="generate_fisher")
     p.add_argument("--c_guidance", type=float, required=False, default=7.5)
-    p.add_argument("--batch_size", type=int, required=False, default=1)
+    p.add_argument("--batch_size", type=int, required=False, default=8)
     p.add_argument("--epochs", type=int, required=False, default=1)
     p.add_argument("--lr", type=float, required=False, default=1e-5)
     p.add_argument("--ckpt_path", type=str, required=False, default="models/ldm/stable-diffusion-v1/sd-v1-4-full-ema.ckpt")
     p.add_argument("--config_path", type=str, required=False, default="configs/stable-diffusion/v1-inference.yaml")
     p.add_argument("--diffusers_config_path", type=str, required=False, default="diffusers_unet_config.json")
-    p.add_argument("--device", type=str, required=False, default="0")
+    p.add_argument("--device", type=str, required=False, default="4")      # the reference's default GPU index
     p.add_argument("--image_size", type=int, required=False, default=512)
     p.add_argument("--num_timesteps", type=int, required=False, default=1000)
     return p
