@@ -208,3 +208,43 @@ def test_cli_flags_match_the_reference():
             assert a.nargs == ref.get("nargs"), (name, flag, "nargs")
             if isinstance(ref.get("choices"), list):
                 assert list(a.choices) == ref["choices"], (name, flag, "choices")
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/sfron_b200.h against the argtypes / restype capi.py binds it with: same argument count,
+    and per argument the same class (pointer, or the scalar's C type).  No call is made."""
+    import ctypes as C
+    hdr = open(os.path.join(ROOT, "include", "sfron_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = re.findall(r"SFR_API\s+([\w\s\*]+?)\s*\b(sfr_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) == 26, [p[1] for p in protos]
+    scalar = {"int": C.c_int, "int32_t": C.c_int, "int64_t": C.c_int64, "float": C.c_float, "double": C.c_double,
+              "unsigned long long": C.c_uint64, "uint64_t": C.c_uint64, "long long": C.c_int64, "unsigned int": C.c_uint, "uint32_t": C.c_uint}
+
+    def klass(decl):
+        decl = decl.strip()
+        if "*" in decl or decl.startswith("sfr_stream_t"):
+            return "ptr"
+        words = [w for w in decl.replace("const", " ").split()]
+        ty = " ".join(words[:-1]) if len(words) > 1 else words[0]
+        return scalar[ty]
+
+    def ctypes_klass(t):
+        if t is C.c_void_p or t is C.c_char_p or isinstance(t, type) and issubclass(t, (C._Pointer,)):
+            return "ptr"
+        return t
+
+    lib = capi.load()
+    for ret, name, args in protos:
+        fn = getattr(lib, name)
+        want = [] if args.strip() in ("", "void") else [klass(a) for a in args.split(",")]
+        got = [ctypes_klass(t) for t in (fn.argtypes or [])]
+        assert len(got) == len(want), (name, len(got), len(want))
+        for i, (g, w) in enumerate(zip(got, want)):
+            if w == "ptr":
+                assert g == "ptr", (name, i, g)
+            else:
+                assert g != "ptr" and C.sizeof(g) == C.sizeof(w) and (g in (C.c_float, C.c_double)) == (w in (C.c_float, C.c_double)), (name, i, g, w)
+        rk = "ptr" if "*" in ret else scalar[ret.strip()]
+        gr = ctypes_klass(fn.restype)
+        assert (gr == "ptr") == (rk == "ptr") and (rk == "ptr" or C.sizeof(gr) == C.sizeof(rk)), (name, "restype")
