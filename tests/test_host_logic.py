@@ -248,3 +248,26 @@ def test_ctypes_signatures_match_the_header():
         rk = "ptr" if "*" in ret else scalar[ret.strip()]
         gr = ctypes_klass(fn.restype)
         assert (gr == "ptr") == (rk == "ptr") and (rk == "ptr" or C.sizeof(gr) == C.sizeof(rk)), (name, "restype")
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """tests/c/abi_consumer.c: the header compiles as pedantic C99, the library links from C, the struct sizes agree with
+    the ctypes mirrors, and without a device the compute entry points return SFR_ERR_NO_DEVICE (no host fallback)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    capi.load()
+    pkg = os.path.dirname(capi.LIB_PATH)
+    exe = str(tmp_path / "abi_consumer")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_consumer.c"), "-o", exe, "-L", pkg,
+                    "-l:" + os.path.basename(capi.LIB_PATH), "-Wl,-rpath," + pkg], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert f"abi {capi.ABI_VERSION}" in out
+    sizes = dict(zip(re.findall(r"(sfr_\w+) \d+", out), map(int, re.findall(r"sfr_\w+ (\d+)", out))))
+    assert sizes == {"sfr_update_args": C.sizeof(capi.UpdateArgs), "sfr_select_state": C.sizeof(capi.SelectState),
+                     "sfr_peer_buf": C.sizeof(capi.PeerBuf), "sfr_peer_geom": C.sizeof(capi.PeerGeom)}, out
+    if not torch.cuda.is_available():
+        assert "no device: info -4 k1 -4 k2a -4" in out and "no CPU fallback" in out
