@@ -307,6 +307,25 @@ def test_k2b_values_on_prefix_boundaries(sfr, dev, prefix):
         assert torch.equal(mask, O.topk_mask_flat(x, k)), (prefix, k)
 
 
+@pytest.mark.parametrize("n", [3_000_000, 24_000_000])
+def test_k2b_ties_spread_over_many_chunks(sfr, dev, n):
+    """One threshold-equal key in EVERY 8192-element chunk, half of them selected (lowest index first).  At 3 M elements the
+    ordered apply ranks them straight from the short tie-chunk list (select.cu kTieListFast); at 24 M the list is longer
+    than that and the two-level scan of the per-chunk counters runs instead.  The select state says which."""
+    g = gen(n)
+    x = torch.randn(n, generator=g) * 1e-2
+    v = float(x.abs().median())
+    x[::8192] = v
+    x[1::16384] = -v                                    # two per chunk in every other chunk, both signs
+    ties = int((x.abs() == v).sum())
+    greater = int((x.abs() > v).sum())
+    k = greater + ties // 2
+    mask, st = run_topk(sfr, dev, x, k)
+    assert st.count_eq == ties and st.tie_budget == ties // 2
+    assert torch.equal(mask, O.topk_mask_flat(x, k))
+    assert int(mask.sum()) == k
+
+
 def test_k2b_all_equal_and_all_zero(sfr, dev):
     for val in (0.0, 2.5):
         x = torch.full((50_000,), val)

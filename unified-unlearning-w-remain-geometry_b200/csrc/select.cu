@@ -135,6 +135,7 @@ select_hist0_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
 //                                 [3] 1 if pass 1 also wrote the provisional mask, [4] that mask's address,
 //                                 [5] number of chunks listed as holding a tie, [6] 1 if that list overflowed
 //                                 (the list lives in the unused tail of the second scratch region),
+//                                 [7] 1 once an ordered apply has walked the list (its counters then need clearing),
 //                                 [8 + r] entries staged in region r
 //   candidate regions             cand_cap words: (flat index << 16) | key[15:0]
 constexpr int64_t kChunkElems = 8192;       // == kChunk below (kApplyThreads * 4 * kChunkVecs)
@@ -462,10 +463,18 @@ __device__ __forceinline__ bool ties_need_order(const sfr_select_state* s) {
 __host__ __device__ inline int64_t tie_list_offset(int64_t nchunks) { return nchunks + (nchunks + 4095) / 4096; }
 __host__ __device__ inline int64_t tie_list_cap(int64_t nchunks) { return 2 * nchunks - tie_list_offset(nchunks); }
 
+// The ordered apply can rank a chunk's ties straight from the tie-chunk list when that list is complete and short:
+// "ties before chunk c" = tie_base + sum of the counters of the listed chunks below c.  That skips the two-level scan of
+// all per-chunk counters (two phases and two grid-wide barriers of the fused apply).  Uniform over the grid.
+constexpr unsigned long long kTieListFast = 2048;
+
 // The candidate list is complete (no region overflowed) and pass 1 left the provisional mask in THIS
 // mask buffer: only the staged candidates (and the chunks that hold an ordered tie) remain to be written.
 __device__ __forceinline__ bool provisional_ok(const unsigned long long* hdr, const uint8_t* mask) {
   return hdr[0] == 0ull && hdr[3] == 1ull && hdr[4] == (unsigned long long)(uintptr_t)mask;
+}
+__device__ __forceinline__ bool tie_list_short(const unsigned long long* hdr, const uint8_t* mask) {
+  return provisional_ok(hdr, mask) && hdr[6] == 0ull && hdr[5] <= kTieListFast;
 }
 
 // Keys of one chunk, all loads issued before the first use.  A chunk is kChunkVecs slabs of
@@ -550,27 +559,37 @@ resolve_candidates_body(int64_t n, const sfr_select_state* __restrict__ state,
   const unsigned int thr16 = state->thr_key & 0xffffu;
   const int regions = (int)hdr[1];
   const unsigned long long cap = hdr[2];
-  // Work item = one quarter of one region; every thread issues its (up to) four list loads before it
-  // touches the mask: the walk is a latency chain otherwise (15 dependent rounds per CTA, 46 us at N3).
-  constexpr int kSplit = 4, kUnroll = 4;
-  const int items = regions * kSplit;
-  for (int w = blockIdx.x; w < items; w += gridDim.x) {
-    const int r = w / kSplit, part = w % kSplit;
+  // Work item = one slice of one region, taken by ONE WARP; a region is cut into as many slices as it takes to give
+  // every warp of the grid about one item.  Each item is a chain of dependent global accesses (count -> entries ->
+  // mask / counters), so what the walk costs is the number of items a warp does one after the other: with CTA-wide
+  // items the 148 CTAs of a small launch each did 16 of them in turn (~30 us at 3.9e7 elements, a third of the select).
+  // Every lane issues its (up to) four list loads before it touches the mask.
+  constexpr int kUnroll = 4;
+  if (regions <= 0) return;
+  const int warps_per_cta = (int)(blockDim.x >> 5);
+  const int total_warps = (int)gridDim.x * warps_per_cta;
+  int split = (total_warps + regions - 1) / regions;
+  split = split < 1 ? 1 : (split > 64 ? 64 : split);
+  const int items = regions * split;
+  const unsigned int lane = threadIdx.x & 31u;
+  // consecutive items go to different CTAs (SMs), then to the next warp of each
+  for (int w = (int)(threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x; w < items; w += total_warps) {
+    const int r = w / split, part = w % split;
     const unsigned long long* region = hdr + kCandHeader + (unsigned long long)r * cap;
     const unsigned int cnt = (unsigned int)hdr[8 + r];
-    const unsigned int per = (cnt + kSplit - 1) / kSplit;
+    const unsigned int per = (cnt + split - 1) / split;
     const unsigned int lo = part * per;
     const unsigned int hi = lo + per < cnt ? lo + per : cnt;
-    for (unsigned int i0 = lo + threadIdx.x; i0 < hi; i0 += blockDim.x * kUnroll) {
+    for (unsigned int i0 = lo + lane; i0 < hi; i0 += 32u * kUnroll) {
       unsigned long long e[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        const unsigned int i = i0 + u * blockDim.x;
+        const unsigned int i = i0 + u * 32u;
         e[u] = i < hi ? __ldcs(region + i) : ~0ull;
       }
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        if (i0 + u * blockDim.x >= hi) continue;
+        if (i0 + u * 32u >= hi) continue;
         const unsigned int low = (unsigned int)(e[u] & 0xffffull);
         if (low == thr16) {
           if (order) {
@@ -713,6 +732,7 @@ template <int MODE>
 __device__ __forceinline__ void
 apply_ordered_body(const float* __restrict__ a, const float* __restrict__ b, float eps,
                    int64_t n, const sfr_select_state* __restrict__ state,
+                   const unsigned long long* __restrict__ tie_base,
                    const unsigned long long* __restrict__ scratch, uint8_t* __restrict__ mask) {
   if (!ties_need_order(state)) return;  // the streaming kernel above wrote the mask
   __shared__ unsigned int warp_tot[kApplyThreads / 32];
@@ -725,6 +745,7 @@ apply_ordered_body(const float* __restrict__ a, const float* __restrict__ b, flo
   const unsigned long long* hdr = scratch + 2 * nchunks;
   const bool only_tie_chunks = provisional_ok(hdr, mask);
   const bool listed = only_tie_chunks && hdr[6] == 0ull;
+  const bool short_list = tie_list_short(hdr, mask);          // then the block bases were never formed
   const unsigned long long* tie_list = scratch + tie_list_offset(nchunks);
   const int64_t visits = listed ? (int64_t)hdr[5] : nchunks;
 
@@ -757,7 +778,17 @@ apply_ordered_body(const float* __restrict__ a, const float* __restrict__ b, flo
     // ties before this chunk = base of its scan block + counts of the earlier chunks of the block
     __shared__ unsigned long long red64[32];
     __shared__ unsigned long long run_s;
-    {
+    if (short_list) {
+      // straight from the list: the counters of the listed chunks below this one (+ the ties of lower ranks)
+      unsigned long long part = 0;
+      for (int64_t j = threadIdx.x; j < visits; j += kApplyThreads) {
+        const unsigned long long other = tie_list[j];
+        if ((int64_t)other < c) part += scratch[other];
+      }
+      part = block_sum<unsigned long long>(part, red64);
+      if (threadIdx.x == 0) run_s = (tie_base ? *tie_base : 0ull) + part;
+      __syncthreads();
+    } else {
       const int64_t blk = c / kScanBlock;
       unsigned long long part = 0;
       for (int64_t i = blk * kScanBlock + threadIdx.x; i < c; i += kApplyThreads) part += scratch[i];
@@ -831,23 +862,27 @@ select_apply_fused_kernel(const float* __restrict__ a, const float* __restrict__
   cg::grid_group grid = cg::this_grid();
   const int64_t nchunks = (n + kChunk - 1) / kChunk;
   const bool order = ties_need_order(state);
-  if (order) {
-    // the per-chunk counters are accumulated into, and the tie-chunk list appended to: clear them first,
-    // so that apply may be repeated after one pass 1
+  unsigned long long* hdr = scratch + 2 * nchunks;
+  if (order && hdr[7] != 0ull) {
+    // an apply has already run on this pass 1's scratch (hdr[7], set below; zeroed with the header by pass 1): the
+    // per-chunk counters are accumulated into and the tie-chunk list appended to, so clear them before walking again
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nchunks; i += (int64_t)gridDim.x * blockDim.x)
       scratch[i] = 0ull;
-    if (blockIdx.x == 0 && threadIdx.x < 2) scratch[2 * nchunks + 5 + threadIdx.x] = 0ull;
+    if (blockIdx.x == 0 && threadIdx.x < 2) hdr[5 + threadIdx.x] = 0ull;
     grid.sync();
   }
   resolve_candidates_body(n, state, scratch, mask);   // list walk: finishes the provisional mask, counts ties
   tie_count_body<MODE>(a, b, eps, n, state, scratch); // (only after a candidate overflow: streaming count)
   if (order) {
-    grid.sync();
-    tie_block_sum_body(nchunks, state, scratch);
-    grid.sync();
-    if (blockIdx.x == 0) tie_block_scan_body(nchunks, state, tie_base, scratch);
-    grid.sync();
-    apply_ordered_body<MODE>(a, b, eps, n, state, scratch, mask);
+    grid.sync();                                       // every CTA has read hdr[7] by now
+    if (blockIdx.x == 0 && threadIdx.x == 0) hdr[7] = 1ull;
+    if (!tie_list_short(hdr, mask)) {                  // long / overflowed list, or no provisional mask: scan every counter
+      tie_block_sum_body(nchunks, state, scratch);
+      grid.sync();
+      if (blockIdx.x == 0) tie_block_scan_body(nchunks, state, tie_base, scratch);
+      grid.sync();
+    }
+    apply_ordered_body<MODE>(a, b, eps, n, state, tie_base, scratch, mask);
   } else {
     apply_stream_body<MODE>(a, b, eps, n, state, scratch, mask);   // returns at once when the walk wrote the mask
   }
