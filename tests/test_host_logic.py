@@ -271,3 +271,45 @@ def test_c_abi_from_plain_c(tmp_path):
                      "sfr_peer_buf": C.sizeof(capi.PeerBuf), "sfr_peer_geom": C.sizeof(capi.PeerGeom)}, out
     if not torch.cuda.is_available():
         assert "no device: info -4 k1 -4 k2a -4" in out and "no CPU fallback" in out
+
+
+def _bench(argv, env_extra=None, timeout=300):
+    import subprocess
+    import sys
+    env = dict(os.environ, **(env_extra or {}))
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + argv, capture_output=True, text=True,
+                          env=env, timeout=timeout, cwd=ROOT)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours): exactly one JSON line on stdout with our
+    arm's metric / unit / config, the bounded sample named, no GPU work claimed; under a multi-rank launch only rank 0
+    works and prints."""
+    import json
+    r = _bench(["--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-elems", str(1 << 18)])
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "sfron_hot_path_GBps" and d["unit"] == "GB/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f32" and d["n_gpus"] == 1
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["elements"] == 675_129_632 and d["config"]["elements_timed"] == 1 << 18
+    assert d["config"]["bytes_per_element"] == 103 and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and str(1 << 18) in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
+    # rank 1 of a 2-rank launch: exits 0 without work and without output
+    r = _bench(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--ref-elems", str(1 << 18)],
+               {"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a machine without a GPU")
+def test_bench_our_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback behind the headline number: without a CUDA device our arm stops with a message, it does not print
+    a line."""
+    r = _bench(["--steps", "1"])
+    assert r.returncode != 0 and r.stdout.strip() == ""
+    assert "no CUDA device" in (r.stderr + r.stdout)
